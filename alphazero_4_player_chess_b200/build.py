@@ -1,0 +1,35 @@
+"""Build the CUDA library in-tree: csrc/*.cu -> libfpc.so (sm_100a only)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libfpc.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+SOURCES = ["fpc_kernels.cu"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--use_fast_math", "-cudart", "shared"]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "fpc.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    cmd = [NVCC, *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB,
+           *[os.path.join(CSRC, s) for s in SOURCES]]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,397 @@
+// Device-side rules of the four-player-chess environment for sm_100a.
+//
+// One WARP owns one game.  The game's board record (include/fpc.h) is staged in shared
+// memory as a 16x16 "mailbox": cell ((row+1)<<4 | (col+1)), every off-board cell and every
+// cut-corner cell holding WALL, so ray walks need no bounds arithmetic.  Rules follow the
+// reference engine; each routine cites the reference lines it reproduces (paths relative to
+// /root/reference/src/cpp).  No piece list is kept: the reference's piece_list_ order is
+// call-history dependent, so lists are produced in canonical order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fpc {
+
+constexpr uint32_t EMPTY = 0x18;  // Piece(false, RED, NO_PIECE), engine/board.h:99
+constexpr uint32_t WALL = 0x1C;   // not a reference value: off-board / cut-corner sentinel
+constexpr int PAWN = 0, KNIGHT = 1, BISHOP = 2, ROOK = 3, QUEEN = 4, KING = 5, NO_PIECE = 6;
+constexpr int NO_SQ = 0xFF;       // mailbox "no square"
+constexpr int MAX_MOVES = 300;    // engine/board.h:706
+constexpr unsigned FULL = 0xffffffffu;
+
+template <int R_, int IA_>
+struct Geo {
+  static constexpr int R = R_, IA = IA_, NSQ = R_ * R_;
+  static constexpr int REC = ((NSQ + 12 + 15) / 16) * 16;
+  static constexpr int OFF_TURN = NSQ, OFF_RIGHTS = NSQ + 1, OFF_KING = NSQ + 5;
+  static constexpr int A = 8 * R_ + 8;            // src/cpp/board.cpp:11
+  static constexpr int ASZ = A * NSQ;             // action_space_size
+  static constexpr int SSZ = 24 * NSQ;            // state_space_size
+  static constexpr int MASK_WORDS = (ASZ + 31) / 32;
+  static constexpr int PLANE_WORDS = (SSZ + 31) / 32;
+  static_assert(R_ <= 14, "mailbox is 16x16 with a one-cell border");
+  static_assert(ASZ % 4 == 0 && SSZ % 4 == 0, "float4 streaming of the dense outputs");
+
+  // engine/board.h:647-654 IsLegalLocation
+  __host__ __device__ static constexpr bool legal(int r, int c) {
+    return (unsigned)r < (unsigned)R && (unsigned)c < (unsigned)R &&
+           !((r < IA || r > R - 1 - IA) && (c < IA || c > R - 1 - IA));
+  }
+  __host__ __device__ static constexpr int mb(int r, int c) { return ((r + 1) << 4) | (c + 1); }
+  __host__ __device__ static constexpr int mb_of_sq(int sq) { return mb(sq / R, sq % R); }
+  __host__ __device__ static constexpr int sq_of_mb(int m) { return ((m >> 4) - 1) * R + (m & 15) - 1; }
+};
+
+__device__ __forceinline__ bool present(uint32_t p) { return (p & 0x80u) != 0; }
+__device__ __forceinline__ int color_of(uint32_t p) { return (p >> 5) & 3; }
+__device__ __forceinline__ int type_of(uint32_t p) { return (p >> 2) & 7; }
+__device__ __forceinline__ int team_of(uint32_t p) { return (p >> 5) & 1; }  // engine/board.h:64-67
+__device__ __forceinline__ uint32_t mk_piece(int color, int type) { return 0x80u | (color << 5) | (type << 2); }
+
+// The 8 queen directions in the reference's action-plane order (move.cpp:13-14, (dcol,drow)):
+// N(0,-1) NW(-1,-1) W(-1,0) SW(-1,1) S(0,1) SE(1,1) E(1,0) NE(1,-1) as mailbox deltas drow*16+dcol.
+// Even = orthogonal, odd = diagonal.
+__device__ __forceinline__ int qdelta(int dir) {
+  return (int)(int8_t)((0xF1011110'0FFFEFF0ull >> (dir * 8)) & 0xff);
+}
+// Knight jumps in plane order (move.cpp:15-16): (dcol,drow) =
+// (-2,-1)(-2,1)(-1,-2)(-1,2)(1,-2)(1,2)(2,-1)(2,1)
+__device__ __forceinline__ int kdcol(int k) { return (int)(int8_t)((0x0202'0101'FFFF'FEFEull >> (k * 8)) & 0xff); }
+__device__ __forceinline__ int kdrow(int k) { return (int)(int8_t)((0x01FF'02FE'02FE'01FFull >> (k * 8)) & 0xff); }
+
+// Per-warp shared-memory scratch.
+template <class G>
+struct alignas(16) WarpScratch {
+  uint32_t mask_bits[G::MASK_WORDS + (4 - G::MASK_WORDS % 4) % 4];   // legal-move mask, 1 bit per action
+  uint32_t plane_bits[G::PLANE_WORDS + (4 - G::PLANE_WORDS % 4) % 4];  // input planes, 1 bit per cell
+  uint32_t moves[MAX_MOVES + 4];  // compact moves: key<<14 | castle<<8 | to_mb, key = flat*8 + promo
+  uint8_t mb[256];                // mailbox board
+  uint8_t rec[256];               // raw record staging (in and out)
+  uint8_t plist[64];              // mailbox squares of the mover's pieces
+  uint8_t rights[4];
+  uint8_t king[4];                // mailbox square per colour, NO_SQ = captured
+  int turn;
+  int pad;
+};
+
+// A move applied "virtually": a -> EMPTY, c -> EMPTY, b -> bp, d -> dp (order of
+// chess::Board::MakeMove, engine/board.cpp:1037-1077).  Unused slots hold 0x1000.
+struct Patch {
+  int a, b, c, d;
+  uint32_t bp, dp;
+};
+
+template <bool PATCHED>
+__device__ __forceinline__ uint32_t cell(const uint8_t *mb, int i, const Patch &p) {
+  uint32_t v = mb[i];
+  if (PATCHED) {
+    if (i == p.a || i == p.c) v = EMPTY;
+    if (i == p.b) v = p.bp;
+    if (i == p.d) v = p.dp;
+  }
+  return v;
+}
+
+// chess::Board::GetAttackers2 with limit 1 == IsAttackedByTeam (engine/board.cpp:606-787).
+// `s` must be an on-board mailbox square.  Rook rays in the reference run to the edge of the
+// R x R box (:632) and bishop rays to the first illegal square (:658); with WALL in the (always
+// empty) cut corners both stop at the same attackers.
+template <class G, bool PATCHED>
+__device__ bool attacked_by_team(const uint8_t *mb, int team, int s, const Patch &p) {
+#pragma unroll
+  for (int dir = 0; dir < 8; ++dir) {
+    const int d = qdelta(dir);
+    int i = s + d;
+    uint32_t v;
+    while ((v = cell<PATCHED>(mb, i, p)) == EMPTY) i += d;
+    if (present(v) && team_of(v) == team) {
+      int t = type_of(v);
+      if (t == QUEEN || t == ((dir & 1) ? BISHOP : ROOK)) return true;
+    }
+  }
+  const int r = (s >> 4) - 1, c = (s & 15) - 1;
+  // knights: all eight squares whatever IA is (:676-694)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int tr = r + kdrow(k), tc = c + kdcol(k);
+    if ((unsigned)tr < (unsigned)G::R && (unsigned)tc < (unsigned)G::R) {
+      uint32_t v = cell<PATCHED>(mb, G::mb(tr, tc), p);
+      if (present(v) && team_of(v) == team && type_of(v) == KNIGHT) return true;
+    }
+  }
+  // pawns (:697-750): RED attacks from the row below, YELLOW from the row above,
+  // BLUE from the column to the left, GREEN from the column to the right.
+  if (team == 0) {
+    const uint32_t red = mk_piece(0, PAWN), yellow = mk_piece(2, PAWN);
+    if (cell<PATCHED>(mb, s + 15, p) == red || cell<PATCHED>(mb, s + 17, p) == red) return true;
+    if (cell<PATCHED>(mb, s - 17, p) == yellow || cell<PATCHED>(mb, s - 15, p) == yellow) return true;
+  } else {
+    const uint32_t blue = mk_piece(1, PAWN), green = mk_piece(3, PAWN);
+    if (cell<PATCHED>(mb, s - 17, p) == blue || cell<PATCHED>(mb, s + 15, p) == blue) return true;
+    if (cell<PATCHED>(mb, s - 15, p) == green || cell<PATCHED>(mb, s + 17, p) == green) return true;
+  }
+  // kings (:753-772)
+#pragma unroll
+  for (int dir = 0; dir < 8; ++dir) {
+    uint32_t v = cell<PATCHED>(mb, s + qdelta(dir), p);
+    if (present(v) && team_of(v) == team && type_of(v) == KING) return true;
+  }
+  return false;
+}
+
+// engine/board.cpp:23-30 + :1474-1524 GetRookLocationType: 0 kingside, 1 queenside, -1 neither.
+template <class G>
+__device__ __forceinline__ int rook_location_type(int color, int sq) {
+  constexpr int R = G::R, IA = G::IA;
+  int ks, qs;
+  switch (color) {
+    case 0: ks = (R - 1) * R + (R - 4); qs = (R - 1) * R + IA; break;
+    case 1: ks = (R - 4) * R; qs = IA * R; break;
+    case 2: ks = IA; qs = R - 4; break;
+    default: ks = IA * R + (R - 1); qs = (R - 4) * R + (R - 1); break;
+  }
+  return sq == ks ? 0 : (sq == qs ? 1 : -1);
+}
+
+// ---- compact move ------------------------------------------------------------------------
+// key = flat*8 + promo (18 bits) in the high bits makes the u32 itself the canonical sort key.
+template <class G>
+__device__ __forceinline__ uint32_t pack_compact(int from_mb, int to_mb, int plane, int promo, int castle) {
+  uint32_t key = (uint32_t)((plane * G::NSQ + G::sq_of_mb(from_mb)) * 8 + promo);
+  return (key << 14) | ((uint32_t)castle << 8) | (uint32_t)to_mb;
+}
+template <class G>
+__device__ __forceinline__ void unpack_compact(uint32_t mv, int &from_mb, int &to_mb, int &plane, int &promo,
+                                               int &castle) {
+  uint32_t key = mv >> 14;
+  promo = key & 7;
+  uint32_t flat = key >> 3;
+  plane = flat / G::NSQ;
+  from_mb = G::mb_of_sq(flat - plane * G::NSQ);
+  to_mb = mv & 0xff;
+  castle = (mv >> 8) & 3;
+}
+
+// Rook squares of a castling move: king steps two cells by u = (to-from)/2; the rook stands
+// 3 (kingside) / 4 (queenside) cells away and lands on from+u (engine/board.cpp:352-461).
+__device__ __forceinline__ void castle_rook(int from_mb, int to_mb, int castle, int &rook_from, int &rook_to) {
+  int u = (to_mb - from_mb) / 2;
+  rook_to = from_mb + u;
+  rook_from = from_mb + u * (castle == 2 ? 3 : 4);  // castle: 1 queenside, 2 kingside
+}
+
+// Work item -> moves.  Item (piece, dir) of the mover's piece at `from`.  Returns the number of
+// pseudo-legal moves of the item and, through the out params, how to enumerate them:
+//   kind 0: to = from + delta*(j+1), plane = plane0 + j      (rays, steps, jumps, pushes)
+//   kind 1: to = from + delta, plane0, promotion N,B,R,Q for j = 0..3 (engine/board.cpp:82-88)
+template <class G>
+__device__ int gen_item(const uint8_t *mb, int from, int dir, int &delta, int &plane0, int &kind) {
+  constexpr int R = G::R;
+  const uint32_t p = mb[from];
+  const int type = type_of(p), color = color_of(p), team = team_of(p);
+  const int r = (from >> 4) - 1, c = (from & 15) - 1;
+  kind = 0;
+  delta = 0;
+  plane0 = 0;
+  switch (type) {
+    case PAWN: {  // engine/board.cpp:97-177 GetPawnMoves2
+      if (dir > 3) return 0;
+      // forward direction as a plane direction: RED N(0) BLUE E(6) YELLOW S(4) GREEN W(2)
+      const int fdir = color == 0 ? 0 : (color == 1 ? 6 : (color == 2 ? 4 : 2));
+      const int fwd = qdelta(fdir);
+      int to, pdir, dist = 1;
+      if (dir == 0) {
+        to = from + fwd;
+        if (mb[to] != EMPTY) return 0;
+        pdir = fdir;
+      } else if (dir == 1) {
+        const bool not_moved = color == 0 ? r == R - 2 : (color == 1 ? c == 1 : (color == 2 ? r == 1 : c == R - 2));
+        if (!not_moved || mb[from + fwd] != EMPTY) return 0;
+        to = from + 2 * fwd;
+        if (mb[to] != EMPTY) return 0;
+        pdir = fdir;
+        dist = 2;
+      } else {
+        // captures on the two forward diagonals, against the other team only (:153-176)
+        // RED: NW(1),NE(7)  YELLOW: SW(3),SE(5)  BLUE: NE(7),SE(5)  GREEN: NW(1),SW(3)
+        const int first = dir == 2;
+        pdir = color == 0 ? (first ? 1 : 7) : (color == 2 ? (first ? 3 : 5) : (color == 1 ? (first ? 7 : 5) : (first ? 1 : 3)));
+        to = from + qdelta(pdir);
+        const uint32_t o = mb[to];
+        if (!present(o) || team_of(o) == team) return 0;
+      }
+      delta = to - from;
+      plane0 = pdir * (R - 1) + dist - 1;
+      // promotion line (:58-76): RED row R/4, YELLOW row 3R/4, BLUE col 3R/4, GREEN col R/4
+      const int tr = (to >> 4) - 1, tc = (to & 15) - 1;
+      const bool promo = color == 0 ? tr == R / 4 : (color == 2 ? tr == 3 * R / 4 : (color == 1 ? tc == 3 * R / 4 : tc == R / 4));
+      if (promo) {
+        kind = 1;
+        return 4;
+      }
+      return 1;
+    }
+    case KNIGHT: {  // engine/board.cpp:179-207: |drow| runs 1..IA-1 only
+      const int dr = kdrow(dir), dc = kdcol(dir);
+      if ((dr < 0 ? -dr : dr) >= G::IA) return 0;
+      const int tr = r + dr, tc = c + dc;
+      if ((unsigned)tr >= (unsigned)R || (unsigned)tc >= (unsigned)R) return 0;
+      const int to = G::mb(tr, tc);
+      const uint32_t o = mb[to];
+      if (o == WALL || (present(o) && team_of(o) == team)) return 0;
+      delta = to - from;
+      plane0 = 8 * (R - 1) + dir;
+      return 1;
+    }
+    case KING: {  // engine/board.cpp:322-341 (castling is a separate item)
+      const int d = qdelta(dir);
+      const uint32_t o = mb[from + d];
+      if (o == WALL || (present(o) && team_of(o) == team)) return 0;
+      delta = d;
+      plane0 = dir * (R - 1);
+      return 1;
+    }
+    case BISHOP:
+      if (!(dir & 1)) return 0;
+      break;
+    case ROOK:
+      if (dir & 1) return 0;
+      break;
+    case QUEEN:
+      break;
+    default:
+      return 0;
+  }
+  // sliders: engine/board.cpp:209-238 AddMovesFromIncrMovement2
+  const int d = qdelta(dir);
+  int i = from + d, cnt = 0;
+  uint32_t o;
+  while ((o = mb[i]) == EMPTY) {
+    ++cnt;
+    i += d;
+  }
+  if (present(o) && team_of(o) != team) ++cnt;
+  delta = d;
+  plane0 = dir * (R - 1);
+  return cnt;
+}
+
+// Castling candidate (engine/board.cpp:343-465).  side: 0 queenside, 1 kingside.  Returns the
+// compact move or 0.  The rook may belong to the partner (:437 compares teams).
+template <class G>
+__device__ uint32_t gen_castle(const uint8_t *mb, int from, int color, uint32_t rights, int side) {
+  constexpr int R = G::R;
+  const bool allowed = side ? (rights >> 6) & 1 : (rights >> 5) & 1;
+  if (!allowed) return 0;
+  // unit step king -> rook: RED ks E(6)/qs W(2), BLUE ks S(4)/qs N(0), YELLOW ks W/qs E, GREEN ks N/qs S
+  const int udir = color == 0 ? (side ? 6 : 2) : (color == 1 ? (side ? 4 : 0) : (color == 2 ? (side ? 2 : 6) : (side ? 0 : 4)));
+  const int u = qdelta(udir);
+  const int nb = side ? 2 : 3;
+  const int r = (from >> 4) - 1, c = (from & 15) - 1;
+  const int ur = (u + 24) / 16 - 1;  // row component of u in {-1,0,1}
+  const int uc = u - ur * 16;
+  const int rr = r + ur * (nb + 1), rc = c + uc * (nb + 1);
+  if ((unsigned)rr >= (unsigned)R || (unsigned)rc >= (unsigned)R) return 0;  // Relative() -> missing (engine/board.h:194-199)
+  const uint32_t rook = mb[from + u * (nb + 1)];
+  if (!present(rook) || type_of(rook) != ROOK || team_of(rook) != (color & 1)) return 0;
+  for (int k = 1; k <= nb; ++k)
+    if (mb[from + u * k] != EMPTY) return 0;
+  Patch none{0x1000, 0x1000, 0x1000, 0x1000, 0, 0};
+  const int other = 1 - (color & 1);
+  if (attacked_by_team<G, false>(mb, other, from + u, none)) return 0;  // :456
+  if (attacked_by_team<G, false>(mb, other, from, none)) return 0;
+  return pack_compact<G>(from, from + 2 * u, udir * (R - 1) + 1, NO_PIECE, side ? 2 : 1);
+}
+
+// src/cpp/board.cpp:59-68 IsKingSafeAfterMove as an attack test on the virtually patched board.
+template <class G>
+__device__ bool king_safe_after(const uint8_t *mb, const uint8_t *king, int turn, uint32_t mv) {
+  int from, to, plane, promo, castle;
+  unpack_compact<G>(mv, from, to, plane, promo, castle);
+  const uint32_t piece = mb[from];
+  Patch p{from, to, 0x1000, 0x1000, piece, 0};
+  if (castle) {
+    castle_rook(from, to, castle, p.c, p.d);
+    p.dp = mb[p.c];
+  }
+  const int ks = type_of(piece) == KING ? to : king[turn];
+  if (ks == NO_SQ) return true;  // engine/board.cpp:945-948
+  return !attacked_by_team<G, true>(mb, 1 - (turn & 1), ks, p);
+}
+
+// Expand a compact move into the reference's 8-byte image (engine/board.h:419-435).
+template <class G>
+__device__ uint64_t expand_move(const uint8_t *mb, const uint8_t *rights, uint32_t mv) {
+  int from, to, plane, promo, castle;
+  unpack_compact<G>(mv, from, to, plane, promo, castle);
+  const uint32_t piece = mb[from];
+  const int type = type_of(piece), color = color_of(piece);
+  const int from_sq = G::sq_of_mb(from), to_sq = G::sq_of_mb(to);
+  uint32_t cap = castle ? EMPTY : mb[to];
+  uint32_t rf = G::NSQ, rt = G::NSQ, r0 = 0, r1 = 0;
+  if (castle) {
+    int a, b;
+    castle_rook(from, to, castle, a, b);
+    rf = G::sq_of_mb(a);
+    rt = G::sq_of_mb(b);
+  }
+  if (type == KING) {  // engine/board.cpp:319-320
+    r0 = rights[color];
+    r1 = 0x80;
+  } else if ((type == ROOK || type == QUEEN) && plane < 8 * (G::R - 1) && !((plane / (G::R - 1)) & 1)) {
+    // engine/board.cpp:262-289 (queens reach it through :304-311)
+    const int ct = rook_location_type<G>(color, from_sq);
+    const uint32_t cur = rights[color];
+    const uint32_t ks = (cur >> 6) & 1, qs = (cur >> 5) & 1;
+    if (ct == 0 && ks) {
+      r0 = cur;
+      r1 = 0x80 | (qs << 5);
+    } else if (ct == 1 && qs) {
+      r0 = cur;
+      r1 = 0x80 | (ks << 6);
+    }
+  }
+  return (uint64_t)from_sq | ((uint64_t)to_sq << 8) | ((uint64_t)cap << 16) | ((uint64_t)promo << 24) |
+         ((uint64_t)rf << 32) | ((uint64_t)rt << 40) | ((uint64_t)r0 << 48) | ((uint64_t)r1 << 56);
+}
+
+// chess::Board::MakeMove (engine/board.cpp:1028-1096) on the mailbox, for a generator move.
+template <class G>
+__device__ __forceinline__ void make_compact(WarpScratch<G> &s, uint32_t mv) {
+  int from, to, plane, promo, castle;
+  unpack_compact<G>(mv, from, to, plane, promo, castle);
+  const int turn = s.turn;
+  const uint32_t piece = s.mb[from], cap = s.mb[to];
+  const int type = type_of(piece);
+  // rights carried by the move (see expand_move)
+  if (type == KING) {
+    s.rights[turn] = 0x80;
+  } else if ((type == ROOK || type == QUEEN) && plane < 8 * (G::R - 1) && !((plane / (G::R - 1)) & 1)) {
+    const int ct = rook_location_type<G>(turn, G::sq_of_mb(from));
+    const uint32_t cur = s.rights[turn];
+    if (ct == 0 && ((cur >> 6) & 1)) s.rights[turn] = 0x80 | (cur & 0x20);
+    else if (ct == 1 && ((cur >> 5) & 1)) s.rights[turn] = 0x80 | (cur & 0x40);
+  }
+  if (present(cap) && type_of(cap) == KING) s.king[color_of(cap)] = NO_SQ;
+  s.mb[from] = EMPTY;
+  s.mb[to] = promo != NO_PIECE ? mk_piece(turn, promo) : piece;
+  if (type == KING) s.king[turn] = to;
+  if (castle) {
+    int rf, rt;
+    castle_rook(from, to, castle, rf, rt);
+    const uint32_t rook = s.mb[rf];
+    s.mb[rf] = EMPTY;
+    s.mb[rt] = rook;
+  }
+  s.turn = (turn + 1) & 3;
+}
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t game, uint64_t ply) {
+  uint64_t z = seed ^ (game * 0x9E3779B97F4A7C15ull) ^ (ply * 0xBF58476D1CE4E5B9ull);
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+}  // namespace fpc

@@ -1,0 +1,785 @@
+// Kernels and C-ABI of the batched four-player-chess environment (sm_100a).
+// See include/fpc.h for the boundary and fpc_device.cuh for the rules.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+
+#include "../../include/fpc.h"
+#include "fpc_device.cuh"
+
+namespace fpc {
+
+constexpr int WARPS_PER_BLOCK = 4;
+
+struct ObserveParams {
+  const uint8_t *boards_in;  // [n][REC]
+  uint8_t *boards_out;       // playout: updated records (may alias boards_in)
+  int n;
+  int need_movegen;
+  uint64_t *moves;      // [n][MAX_MOVES] or null
+  int32_t *flat;        // [n][MAX_MOVES] or null
+  int32_t *counts;      // [n] or null
+  int32_t *status;      // [n] or null
+  float *planes;        // [n][24][R][R] or null
+  const int32_t *k;     // [n] or null
+  int k_all;            // -1: own turn
+  float *mask;          // [n][A][R][R] or null
+  // playout
+  int playout;
+  uint64_t seed;
+  uint64_t *game;
+  int32_t *ply;
+  const uint8_t *start;
+  int max_plies;
+  uint64_t game_stride;
+  uint64_t *chosen;
+  unsigned long long *counters;
+};
+
+template <class G>
+__device__ __forceinline__ void load_record(WarpScratch<G> &s, const uint8_t *rec_g, int lane) {
+  // mailbox <- WALL; record -> staging (coalesced 16-byte loads: the record is contiguous)
+  reinterpret_cast<uint2 *>(s.mb)[lane] = make_uint2(0x1C1C1C1Cu, 0x1C1C1C1Cu);
+  if (lane < G::REC / 16)
+    reinterpret_cast<uint4 *>(s.rec)[lane] = reinterpret_cast<const uint4 *>(rec_g)[lane];  // may be updated in place: no __ldg
+  if (lane < 4) s.king[lane] = NO_SQ;
+  __syncwarp();
+  if (lane < 4) s.rights[lane] = s.rec[G::OFF_RIGHTS + lane];
+  if (lane == 0) s.turn = s.rec[G::OFF_TURN] & 3;
+  for (int sq = lane; sq < G::NSQ; sq += 32) {
+    const int r = sq / G::R, c = sq - r * G::R;
+    if (G::legal(r, c)) {
+      const uint32_t p = s.rec[sq];
+      s.mb[G::mb(r, c)] = (uint8_t)p;
+      if (present(p) && type_of(p) == KING) s.king[color_of(p)] = (uint8_t)G::mb(r, c);
+    }
+  }
+  __syncwarp();
+}
+
+template <class G>
+__device__ __forceinline__ void store_record(WarpScratch<G> &s, uint8_t *rec_g, int lane) {
+  for (int sq = lane; sq < G::REC; sq += 32) {
+    uint32_t v = 0;
+    if (sq < G::NSQ) {
+      const int r = sq / G::R, c = sq - r * G::R;
+      v = G::legal(r, c) ? s.mb[G::mb(r, c)] : EMPTY;
+    } else if (sq == G::OFF_TURN) {
+      v = s.turn;
+    } else if (sq < G::OFF_KING) {
+      v = s.rights[sq - G::OFF_RIGHTS];
+    } else if (sq < G::OFF_KING + 4) {
+      const int k = s.king[sq - G::OFF_KING];
+      v = k == NO_SQ ? G::NSQ : G::sq_of_mb(k);
+    }
+    s.rec[sq] = (uint8_t)v;
+  }
+  __syncwarp();
+  if (lane < G::REC / 16) reinterpret_cast<uint4 *>(rec_g)[lane] = reinterpret_cast<const uint4 *>(s.rec)[lane];
+}
+
+// Stream one bit-plane set out as dense f32 (0.0 / 1.0): every warp store instruction
+// covers 512 contiguous bytes.
+template <int NFLOATS>
+__device__ __forceinline__ void stream_bits_as_f32(const uint32_t *bits, float *dst, int lane) {
+  constexpr int NF4 = NFLOATS / 4;
+  float4 *out = reinterpret_cast<float4 *>(dst);
+#pragma unroll 4
+  for (int f4 = lane; f4 < NF4; f4 += 32) {
+    const uint32_t nib = (bits[f4 >> 3] >> ((f4 & 7) * 4)) & 15u;
+    float4 v;
+    v.x = (nib & 1u) ? 1.0f : 0.0f;
+    v.y = (nib & 2u) ? 1.0f : 0.0f;
+    v.z = (nib & 4u) ? 1.0f : 0.0f;
+    v.w = (nib & 8u) ? 1.0f : 0.0f;
+    __stcs(out + f4, v);
+  }
+}
+
+template <class G>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) observe_kernel(const __grid_constant__ ObserveParams P) {
+  __shared__ WarpScratch<G> scratch[WARPS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = blockIdx.x * WARPS_PER_BLOCK + wib;
+  if (g >= P.n) return;
+  WarpScratch<G> &s = scratch[wib];
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  if (P.mask)
+    for (int i = lane; i < G::MASK_WORDS; i += 32) s.mask_bits[i] = 0;
+  if (P.planes)
+    for (int i = lane; i < G::PLANE_WORDS; i += 32) s.plane_bits[i] = 0;
+  load_record<G>(s, P.boards_in + (size_t)g * G::REC, lane);
+  const int turn = s.turn;
+
+  // ---- piece scan: mover's piece list + input-plane bits (src/cpp/board.cpp:318-344) -----
+  int rot = 0;
+  if (P.planes) {
+    rot = P.k ? P.k[g] : (P.k_all < 0 ? turn : P.k_all);
+    rot &= 3;
+  }
+  int np = 0;
+  for (int base = 0; base < G::NSQ; base += 32) {
+    const int sq = base + lane;
+    uint32_t p = EMPTY;
+    int r = 0, c = 0;
+    if (sq < G::NSQ) {
+      r = sq / G::R;
+      c = sq - r * G::R;
+      if (G::legal(r, c)) p = s.mb[G::mb(r, c)];
+    }
+    const bool mine = present(p) && color_of(p) == turn;
+    const unsigned b = __ballot_sync(FULL, mine);
+    if (mine) {
+      const int idx = np + __popc(b & lt_mask);
+      if (idx < 64) s.plist[idx] = (uint8_t)G::mb(r, c);
+    }
+    np += __popc(b);
+    if (P.planes && present(p)) {
+      // ch = ((color - turn) mod 4)*6 + type - 1, -1 wrapping to 23 (src/cpp/board.cpp:336)
+      int ch = ((color_of(p) - turn) & 3) * 6 + type_of(p) - 1;
+      if (ch < 0) ch += 24;
+      // torch.rot90(k) on the last two dims: one quarter turn sends (r,c) -> (R-1-c, r)
+      int rr = r, cc = c;
+      for (int t = 0; t < rot; ++t) {
+        const int nr = G::R - 1 - cc;
+        cc = rr;
+        rr = nr;
+      }
+      const int bit = ch * G::NSQ + rr * G::R + cc;
+      atomicOr(&s.plane_bits[bit >> 5], 1u << (bit & 31));
+    }
+  }
+  if (np > 64) np = 64;
+  __syncwarp();
+
+  int n_legal = 0, status = 0;
+  uint32_t chosen_mv = 0;
+  if (P.need_movegen) {
+    const int king_sq = s.king[turn];
+    // ---- pseudo-legal generation (engine/board.cpp:846-889); nothing without a king ------
+    int n_pseudo = 0;
+    bool overflow = false;
+    if (king_sq != NO_SQ) {
+      const int items = np * 8;
+      for (int base = 0; base < items; base += 32) {
+        const int item = base + lane;
+        int cnt = 0, delta = 0, plane0 = 0, kind = 0, from = 0;
+        if (item < items) {
+          from = s.plist[item >> 3];
+          cnt = gen_item<G>(s.mb, from, item & 7, delta, plane0, kind);
+        }
+        // exclusive prefix sum of cnt over the warp
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(FULL, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        int at = n_pseudo + incl - cnt;
+        if (n_pseudo + total > MAX_MOVES) {
+          overflow = true;
+        } else {
+          for (int j = 0; j < cnt; ++j) {
+            uint32_t mv;
+            if (kind == 0) mv = pack_compact<G>(from, from + delta * (j + 1), plane0 + j, NO_PIECE, 0);
+            else mv = pack_compact<G>(from, from + delta, plane0, KNIGHT + j, 0);
+            s.moves[at + j] = mv;
+          }
+          n_pseudo += total;
+        }
+      }
+      // castling: two candidates, each needs two attack tests (engine/board.cpp:343-465)
+      {
+        uint32_t mv = 0;
+        if (lane < 2) mv = gen_castle<G>(s.mb, king_sq, turn, s.rights[turn], lane);
+        const unsigned b = __ballot_sync(FULL, mv != 0);
+        if (b) {
+          if (n_pseudo + __popc(b) > MAX_MOVES) {
+            overflow = true;
+          } else {
+            if (mv) s.moves[n_pseudo + __popc(b & lt_mask)] = mv;
+            n_pseudo += __popc(b);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- legal filter (src/cpp/board.cpp:94-118), compacted in place -----------------------
+    bool takes_king = false;
+    for (int base = 0; base < n_pseudo; base += 32) {
+      const int i = base + lane;
+      uint32_t mv = 0;
+      bool ok = false;
+      if (i < n_pseudo) {
+        mv = s.moves[i];
+        ok = king_safe_after<G>(s.mb, s.king, turn, mv);
+        if (ok) {
+          const uint32_t cap = s.mb[mv & 0xff];
+          if (((mv >> 8) & 3) == 0 && present(cap) && type_of(cap) == KING) takes_king = true;
+        }
+      }
+      const unsigned b = __ballot_sync(FULL, ok);
+      __syncwarp();
+      if (ok) s.moves[n_legal + __popc(b & lt_mask)] = mv;
+      n_legal += __popc(b);
+    }
+    __syncwarp();
+    takes_king = __any_sync(FULL, takes_king);
+
+    // ---- result (engine/board.cpp:891-939, order-independent contract) ---------------------
+    const bool ry = (turn & 1) == 0;
+    int result = 0;
+    if (king_sq == NO_SQ) {
+      result = ry ? 2 : 1;
+    } else if (n_legal == 0) {
+      Patch none{0x1000, 0x1000, 0x1000, 0x1000, 0, 0};
+      const bool in_check = attacked_by_team<G, false>(s.mb, 1 - (turn & 1), king_sq, none);
+      result = in_check ? (ry ? 2 : 1) : 3;
+      if (in_check) status |= FPC_STATUS_IN_CHECK;
+    }
+    status |= result;
+    if (takes_king) status |= FPC_STATUS_CAN_TAKE_KING;
+    if (overflow) status |= FPC_STATUS_OVERFLOW;
+
+    // ---- canonical order: rank = number of smaller keys (keys are unique) ------------------
+    uint32_t pick = 0xffffffffu;
+    if (P.playout && result == 0)
+      pick = (uint32_t)(((mix64(P.seed, P.game[g], (uint64_t)P.ply[g]) >> 32) * (uint64_t)n_legal) >> 32);
+    const bool want_lists = P.moves || P.flat;
+    if (want_lists || P.mask || P.playout) {
+      for (int base = 0; base < n_legal; base += 32) {
+        const int i = base + lane;
+        if (i < n_legal) {
+          const uint32_t mv = s.moves[i];
+          const uint32_t flat = mv >> 17;
+          if (P.mask) atomicOr(&s.mask_bits[flat >> 5], 1u << (flat & 31));
+          if (want_lists || P.playout) {
+            int rank = 0;
+            for (int j = 0; j < n_legal; ++j) rank += s.moves[j] < mv;
+            if (P.moves) P.moves[(size_t)g * MAX_MOVES + rank] = expand_move<G>(s.mb, s.rights, mv);
+            if (P.flat) P.flat[(size_t)g * MAX_MOVES + rank] = (int32_t)flat;
+            if ((uint32_t)rank == pick) chosen_mv = mv;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      if (P.counts) P.counts[g] = n_legal;
+    }
+  }
+
+  // ---- dense outputs ---------------------------------------------------------------------
+  if (P.planes) stream_bits_as_f32<G::SSZ>(s.plane_bits, P.planes + (size_t)g * G::SSZ, lane);
+  if (P.mask) stream_bits_as_f32<G::ASZ>(s.mask_bits, P.mask + (size_t)g * G::ASZ, lane);
+
+  // ---- playout: play the chosen move or re-seed the slot ------------------------------------
+  if (P.playout) {
+    const unsigned who = __ballot_sync(FULL, chosen_mv != 0);
+    const int result = status & FPC_STATUS_RESULT_MASK;
+    const int ply = P.ply[g];
+    uint64_t chosen64 = 0;
+    bool finished = false;
+    if (result == 0 && who) {
+      const uint32_t mv = __shfl_sync(FULL, chosen_mv, __ffs(who) - 1);
+      if (P.chosen) chosen64 = expand_move<G>(s.mb, s.rights, mv);
+      __syncwarp();
+      if (lane == 0) make_compact<G>(s, mv);
+      __syncwarp();
+      if (ply + 1 >= P.max_plies) finished = true;
+    } else {
+      finished = true;
+    }
+    if (finished) {
+      status |= FPC_STATUS_FINISHED;
+      if (lane < G::REC / 16)
+        reinterpret_cast<uint4 *>(P.boards_out + (size_t)g * G::REC)[lane] =
+            __ldg(reinterpret_cast<const uint4 *>(P.start) + lane);
+    } else {
+      store_record<G>(s, P.boards_out + (size_t)g * G::REC, lane);
+    }
+    if (lane == 0) {
+      if (P.chosen) P.chosen[g] = chosen64;
+      if (finished) {
+        P.game[g] += P.game_stride;
+        P.ply[g] = 0;
+      } else {
+        P.ply[g] = ply + 1;
+      }
+      if (P.counters) {
+        atomicAdd(&P.counters[0], 1ull);
+        atomicAdd(&P.counters[6], (unsigned long long)n_legal);
+        if (finished) {
+          atomicAdd(&P.counters[1], 1ull);
+          atomicAdd(&P.counters[2 + result], 1ull);
+        }
+        if (status & FPC_STATUS_OVERFLOW) atomicAdd(&P.counters[7], 1ull);
+      }
+    }
+  }
+  if (lane == 0 && P.status) P.status[g] = status;
+}
+
+// chess::Board::MakeMove (engine/board.cpp:1028-1096) for arbitrary 8-byte moves, or for
+// index-built moves (src/cpp/move.cpp:41-61) when flat != null.  Works on the record bytes.
+template <class G>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+    make_kernel(const uint8_t *in, const uint64_t *moves, const int32_t *flat, int n, uint8_t *out, int32_t *err) {
+  __shared__ alignas(16) uint8_t recs[WARPS_PER_BLOCK][256];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = blockIdx.x * WARPS_PER_BLOCK + wib;
+  if (g >= n) return;
+  uint8_t *b = recs[wib];
+  if (lane < G::REC / 16)
+    reinterpret_cast<uint4 *>(b)[lane] = reinterpret_cast<const uint4 *>(in + (size_t)g * G::REC)[lane];
+  __syncwarp();
+  if (lane == 0) {
+    constexpr int R = G::R, NSQ = G::NSQ;
+    int from, to, promo = NO_PIECE, rf = NSQ, rt = NSQ;
+    uint32_t r1 = 0;
+    int code = FPC_OK;
+    if (flat && (flat[g] < 0 || flat[g] >= G::ASZ)) {
+      from = to = NSQ;
+    } else if (flat) {
+      // Move(int flat_index): from = pos, to = from.Relative(...) (move.cpp:41-61)
+      const int f = flat[g];
+      const int type = f / NSQ, pos = f - type * NSQ;
+      const int row = pos / R, col = pos - row * R;
+      int dr, dc;
+      if (type < 8 * (R - 1)) {
+        const int dir = type / (R - 1), dist = type - dir * (R - 1) + 1;
+        const int d = qdelta(dir);
+        const int ur = (d + 24) / 16 - 1, uc = d - ur * 16;
+        dr = ur * dist;
+        dc = uc * dist;
+      } else {
+        int k = type - 8 * (R - 1);
+        if (k > 7) k = 7;
+        dr = kdrow(k);
+        dc = kdcol(k);
+      }
+      const int tr = row + dr, tc = col + dc;
+      from = pos;
+      to = ((unsigned)tr < (unsigned)R && (unsigned)tc < (unsigned)R) ? tr * R + tc : NSQ;
+    } else {
+      const uint64_t m = moves[g];
+      from = (int)(m & 0xff);
+      to = (int)((m >> 8) & 0xff);
+      promo = (int)((m >> 24) & 0xff);
+      rf = (int)((m >> 32) & 0xff);
+      rt = (int)((m >> 40) & 0xff);
+      r1 = (uint32_t)((m >> 56) & 0xff);
+    }
+    if (from >= NSQ || to >= NSQ) {
+      code = FPC_ERR_MOVE;  // off-board squares: undefined behaviour in the reference
+    } else {
+      const int turn = b[G::OFF_TURN] & 3;
+      const uint32_t piece = b[from], cap = b[to];
+      if (present(cap)) {  // RemovePiece(to), :1040-1044
+        b[to] = EMPTY;
+        if (type_of(cap) == KING) b[G::OFF_KING + color_of(cap)] = NSQ;
+      }
+      if (!present(piece)) {
+        code = FPC_ERR_MOVE;  // thrown after the capture was removed (:1046-1054)
+      } else {
+        b[from] = EMPTY;
+        if (type_of(piece) == KING) b[G::OFF_KING + color_of(piece)] = NSQ;
+        const uint32_t placed = promo != NO_PIECE ? mk_piece(turn, promo & 7) : piece;  // :1057-1067
+        b[to] = (uint8_t)placed;
+        if (type_of(placed) == KING) b[G::OFF_KING + color_of(placed)] = (uint8_t)to;
+        if (rf < NSQ && rt < NSQ) {  // :1070-1077
+          const uint32_t rook = b[rf];
+          b[rf] = EMPTY;
+          b[rt] = (uint8_t)rook;
+        }
+        if (r1 & 0x80) b[G::OFF_RIGHTS + turn] = (uint8_t)r1;  // :1080-1084
+        b[G::OFF_TURN] = (uint8_t)((turn + 1) & 3);             // :1088
+      }
+    }
+    if (err) err[g] = code;
+  }
+  __syncwarp();
+  if (lane < G::REC / 16)
+    reinterpret_cast<uint4 *>(out + (size_t)g * G::REC)[lane] = reinterpret_cast<const uint4 *>(b)[lane];
+}
+
+// chess::Board::CalculateHeuristic (engine/board.cpp:1263-1292) for the team to move.
+template <class G>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) heuristic_kernel(const uint8_t *in, int n, int32_t *value) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = blockIdx.x * WARPS_PER_BLOCK + wib;
+  if (g >= n) return;
+  const uint8_t *b = in + (size_t)g * G::REC;
+  const int team = b[G::OFF_TURN] & 1;
+  int h = 0;
+  for (int sq = lane; sq < G::NSQ; sq += 32) {
+    const uint32_t p = b[sq];
+    if (present(p) && type_of(p) != KING) {
+      const int t = type_of(p);
+      const int v = t == PAWN ? 1 : (t == ROOK ? 5 : (t == QUEEN ? 9 : 3));
+      h += team_of(p) == team ? v : -v;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(FULL, h, o);
+  if (lane == 0) value[g] = h;
+}
+
+// ---- host side ----------------------------------------------------------------------------
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+static int cuda_check(cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return FPC_OK;
+  return fail(FPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <class G>
+static int launch_observe(const ObserveParams &p, cudaStream_t st) {
+  if (p.n == 0) return FPC_OK;
+  const int blocks = (p.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  observe_kernel<G><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
+  return cuda_check(cudaGetLastError(), "observe_kernel launch");
+}
+template <class G>
+static int launch_make(const uint8_t *in, const uint64_t *moves, const int32_t *flat, int n, uint8_t *out,
+                       int32_t *err, cudaStream_t st) {
+  if (n == 0) return FPC_OK;
+  const int blocks = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  make_kernel<G><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(in, moves, flat, n, out, err);
+  return cuda_check(cudaGetLastError(), "make_kernel launch");
+}
+template <class G>
+static int launch_heuristic(const uint8_t *in, int n, int32_t *v, cudaStream_t st) {
+  if (n == 0) return FPC_OK;
+  const int blocks = (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  heuristic_kernel<G><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(in, n, v);
+  return cuda_check(cudaGetLastError(), "heuristic_kernel launch");
+}
+
+#define FPC_DISPATCH(R, CALL)                                              \
+  switch (R) {                                                             \
+    case 14: { using G = Geo<14, 3>; return CALL; }                        \
+    case 13: { using G = Geo<13, 3>; return CALL; }                        \
+    case 10: { using G = Geo<10, 2>; return CALL; }                        \
+    case 8: { using G = Geo<8, 2>; return CALL; }                          \
+    default: return fail(FPC_ERR_ARG, "unsupported board size R=" + std::to_string(R)); \
+  }
+
+static int ia_of(int R) { return R == 14 || R == 13 ? 3 : (R == 10 || R == 8 ? 2 : -1); }
+
+static int do_observe(int R, const ObserveParams &p, cudaStream_t st) { FPC_DISPATCH(R, launch_observe<G>(p, st)); }
+static int do_make(int R, const uint8_t *in, const uint64_t *moves, const int32_t *flat, int n, uint8_t *out,
+                   int32_t *err, cudaStream_t st) {
+  FPC_DISPATCH(R, launch_make<G>(in, moves, flat, n, out, err, st));
+}
+static int do_heuristic(int R, const uint8_t *in, int n, int32_t *v, cudaStream_t st) {
+  FPC_DISPATCH(R, launch_heuristic<G>(in, n, v, st));
+}
+
+}  // namespace fpc
+
+using namespace fpc;
+
+extern "C" {
+
+const char *fpc_last_error(void) { return g_err.c_str(); }
+int fpc_version(void) { return 100; }
+int fpc_supported(int R) { return ia_of(R) > 0; }
+int fpc_invalid_area(int R) { return ia_of(R); }
+int fpc_record_bytes(int R) { return fpc_supported(R) ? ((R * R + 12 + 15) / 16) * 16 : FPC_ERR_ARG; }
+int fpc_num_action_channels(int R) { return fpc_supported(R) ? 8 * R + 8 : FPC_ERR_ARG; }
+int fpc_action_space_size(int R) { return fpc_supported(R) ? (8 * R + 8) * R * R : FPC_ERR_ARG; }
+int fpc_state_space_size(int R) { return fpc_supported(R) ? 24 * R * R : FPC_ERR_ARG; }
+
+static const int kQd[8][2] = {{0, -1}, {-1, -1}, {-1, 0}, {-1, 1}, {0, 1}, {1, 1}, {1, 0}, {1, -1}};   // move.cpp:13-14
+static const int kKd[8][2] = {{-2, -1}, {-2, 1}, {-1, -2}, {-1, 2}, {1, -2}, {1, 2}, {2, -1}, {2, 1}}; // move.cpp:15-16
+
+uint64_t fpc_move_from_flat(int R, int flat) {
+  const int nsq = R * R;
+  if (!fpc_supported(R) || flat < 0 || flat >= (8 * R + 8) * nsq) {
+    fail(FPC_ERR_ARG, "flat index out of range");
+    return ~0ull;
+  }
+  const int type = flat / nsq, pos = flat % nsq, row = pos / R, col = pos % R;
+  int dr, dc;
+  if (type < 8 * (R - 1)) {
+    const int dir = type / (R - 1), dist = type % (R - 1) + 1;
+    dc = kQd[dir][0] * dist;
+    dr = kQd[dir][1] * dist;
+  } else {
+    int k = type - 8 * (R - 1);
+    if (k > 7) k = 7;
+    dc = kKd[k][0];
+    dr = kKd[k][1];
+  }
+  const int tr = row + dr, tc = col + dc;
+  const uint64_t to = (tr < 0 || tr >= R || tc < 0 || tc >= R) ? nsq : tr * R + tc;
+  return (uint64_t)pos | (to << 8) | (0x18ull << 16) | (6ull << 24) | ((uint64_t)nsq << 32) | ((uint64_t)nsq << 40);
+}
+
+int fpc_move_flat_index(int R, uint64_t move) {
+  if (!fpc_supported(R)) return fail(FPC_ERR_ARG, "unsupported board size");
+  const int from = (int)(move & 0xff), to = (int)((move >> 8) & 0xff);
+  // BoardLocation::GetRow/GetCol (engine/board.h:203-204) also decode the "missing" value R*R
+  const int dx = to % R - from % R, dy = to / R - from / R;
+  int plane = -1;
+  for (int i = 0; i < 8 && plane < 0; ++i)
+    for (int d = 1; d <= R - 1; ++d)
+      if (dx == kQd[i][0] * d && dy == kQd[i][1] * d) { plane = i * (R - 1) + d - 1; break; }
+  for (int i = 0; i < 8 && plane < 0; ++i)
+    if (dx == kKd[i][0] && dy == kKd[i][1]) plane = 8 * (R - 1) + i;
+  if (plane < 0) return -1;
+  return plane * R * R + (from / R) * R + from % R;
+}
+
+int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_t *d_flat, int32_t *d_counts,
+                int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all, float *d_mask, void *stream) {
+  if (n < 0 || (n > 0 && !d_boards)) return fail(FPC_ERR_ARG, "fpc_observe: bad boards/n");
+  ObserveParams p{};
+  p.boards_in = d_boards;
+  p.n = n;
+  p.need_movegen = (d_moves || d_flat || d_counts || d_status || d_mask) ? 1 : 0;
+  p.moves = d_moves;
+  p.flat = d_flat;
+  p.counts = d_counts;
+  p.status = d_status;
+  p.planes = d_planes;
+  p.k = d_k;
+  p.k_all = k_all;
+  p.mask = d_mask;
+  return do_observe(R, p, (cudaStream_t)stream);
+}
+
+int fpc_encode(int R, const uint8_t *d_boards, int n, const int32_t *d_k, int k_all, float *d_planes, void *stream) {
+  if (!d_planes && n > 0) return fail(FPC_ERR_ARG, "fpc_encode: null output");
+  return fpc_observe(R, d_boards, n, nullptr, nullptr, nullptr, nullptr, d_planes, d_k, k_all, nullptr, stream);
+}
+
+int fpc_make_moves(int R, const uint8_t *d_in, const uint64_t *d_moves, int n, uint8_t *d_out, int32_t *d_err,
+                   void *stream) {
+  if (n < 0 || (n > 0 && (!d_in || !d_moves || !d_out))) return fail(FPC_ERR_ARG, "fpc_make_moves: bad argument");
+  return do_make(R, d_in, d_moves, nullptr, n, d_out, d_err, (cudaStream_t)stream);
+}
+
+int fpc_make_index(int R, const uint8_t *d_in, const int32_t *d_flat, int n, uint8_t *d_out, int32_t *d_err,
+                   void *stream) {
+  if (n < 0 || (n > 0 && (!d_in || !d_flat || !d_out))) return fail(FPC_ERR_ARG, "fpc_make_index: bad argument");
+  return do_make(R, d_in, nullptr, d_flat, n, d_out, d_err, (cudaStream_t)stream);
+}
+
+int fpc_heuristic(int R, const uint8_t *d_boards, int n, int32_t *d_value, void *stream) {
+  if (n < 0 || (n > 0 && (!d_boards || !d_value))) return fail(FPC_ERR_ARG, "fpc_heuristic: bad argument");
+  return do_heuristic(R, d_boards, n, d_value, (cudaStream_t)stream);
+}
+
+int fpc_playout_step(int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d_game, int32_t *d_ply,
+                     const uint8_t *d_start, int max_plies, uint64_t game_stride, uint64_t *d_chosen,
+                     int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all,
+                     float *d_mask, uint64_t *d_counters, void *stream) {
+  if (n < 0 || (n > 0 && (!d_boards || !d_game || !d_ply || !d_start)) || max_plies <= 0)
+    return fail(FPC_ERR_ARG, "fpc_playout_step: bad argument");
+  ObserveParams p{};
+  p.boards_in = d_boards;
+  p.boards_out = d_boards;
+  p.n = n;
+  p.need_movegen = 1;
+  p.counts = d_counts;
+  p.status = d_status;
+  p.planes = d_planes;
+  p.k = d_k;
+  p.k_all = k_all;
+  p.mask = d_mask;
+  p.playout = 1;
+  p.seed = seed;
+  p.game = d_game;
+  p.ply = d_ply;
+  p.start = d_start;
+  p.max_plies = max_plies;
+  p.game_stride = game_stride;
+  p.chosen = d_chosen;
+  p.counters = reinterpret_cast<unsigned long long *>(d_counters);
+  return do_observe(R, p, (cudaStream_t)stream);
+}
+
+// ---- host-buffer context ---------------------------------------------------------------------
+
+struct fpc_ctx {
+  int device, R, max_n, rec;
+  cudaStream_t stream;
+  uint8_t *d_boards, *d_boards2, *d_start;
+  uint64_t *d_moves, *d_game;
+  int32_t *d_flat, *d_counts, *d_status, *d_ply, *d_err;
+  float *d_planes, *d_mask;   // lazily allocated for host-destination dense outputs
+};
+
+#define CK(expr)                                   \
+  do {                                             \
+    int rc_ = cuda_check((expr), #expr);           \
+    if (rc_ != FPC_OK) return rc_;                 \
+  } while (0)
+
+fpc_ctx *fpc_ctx_create(int device, int R, int max_n) {
+  if (!fpc_supported(R) || max_n <= 0) {
+    fail(FPC_ERR_ARG, "fpc_ctx_create: bad argument");
+    return nullptr;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+    fail(FPC_ERR_CUDA, "fpc_ctx_create: no usable CUDA device (there is no CPU fallback)");
+    return nullptr;
+  }
+  if (cuda_check(cudaSetDevice(device), "cudaSetDevice") != FPC_OK) return nullptr;
+  fpc_ctx *c = new fpc_ctx();
+  memset(c, 0, sizeof *c);
+  c->device = device;
+  c->R = R;
+  c->max_n = max_n;
+  c->rec = fpc_record_bytes(R);
+  const size_t n = (size_t)max_n;
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_boards, n * c->rec) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_boards2, n * c->rec) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_start, c->rec) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_moves, n * FPC_MAX_MOVES * sizeof(uint64_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_flat, n * FPC_MAX_MOVES * sizeof(int32_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_game, n * sizeof(uint64_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_counts, n * sizeof(int32_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_status, n * sizeof(int32_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_ply, n * sizeof(int32_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&c->d_err, n * sizeof(int32_t)) == cudaSuccess;
+  if (!ok) {
+    fail(FPC_ERR_CUDA, std::string("fpc_ctx_create: ") + cudaGetErrorString(cudaGetLastError()));
+    fpc_ctx_destroy(c);
+    return nullptr;
+  }
+  return c;
+}
+
+void fpc_ctx_destroy(fpc_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  cudaFree(c->d_boards);
+  cudaFree(c->d_boards2);
+  cudaFree(c->d_start);
+  cudaFree(c->d_moves);
+  cudaFree(c->d_flat);
+  cudaFree(c->d_game);
+  cudaFree(c->d_counts);
+  cudaFree(c->d_status);
+  cudaFree(c->d_ply);
+  cudaFree(c->d_err);
+  cudaFree(c->d_planes);
+  cudaFree(c->d_mask);
+  delete c;
+}
+
+void *fpc_ctx_stream(fpc_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+static int ctx_check(fpc_ctx *c, int n, const char *who) {
+  if (!c) return fail(FPC_ERR_ARG, std::string(who) + ": null context");
+  if (n < 0 || n > c->max_n) return fail(FPC_ERR_ARG, std::string(who) + ": n exceeds the context capacity");
+  return cuda_check(cudaSetDevice(c->device), "cudaSetDevice");
+}
+
+int fpc_host_observe(fpc_ctx *c, const uint8_t *h_boards, int n, uint64_t *h_moves, int32_t *h_flat,
+                     int32_t *h_counts, int32_t *h_status, float *h_planes, float *d_planes, int k_all,
+                     float *h_mask, float *d_mask) {
+  int rc = ctx_check(c, n, "fpc_host_observe");
+  if (rc != FPC_OK) return rc;
+  if (n == 0) return FPC_OK;
+  if (!h_boards) return fail(FPC_ERR_ARG, "fpc_host_observe: null boards");
+  const size_t N = (size_t)n;
+  const size_t ssz = (size_t)fpc_state_space_size(c->R), asz = (size_t)fpc_action_space_size(c->R);
+  if (h_planes && !d_planes) {
+    if (!c->d_planes) CK(cudaMalloc(&c->d_planes, (size_t)c->max_n * ssz * sizeof(float)));
+    d_planes = c->d_planes;
+  }
+  if (h_mask && !d_mask) {
+    if (!c->d_mask) CK(cudaMalloc(&c->d_mask, (size_t)c->max_n * asz * sizeof(float)));
+    d_mask = c->d_mask;
+  }
+  CK(cudaMemcpyAsync(c->d_boards, h_boards, N * c->rec, cudaMemcpyHostToDevice, c->stream));
+  rc = fpc_observe(c->R, c->d_boards, n, h_moves ? c->d_moves : nullptr, h_flat ? c->d_flat : nullptr,
+                   (h_counts || h_moves || h_flat) ? c->d_counts : nullptr, h_status ? c->d_status : nullptr,
+                   d_planes, nullptr, k_all, d_mask, c->stream);
+  if (rc != FPC_OK) return rc;
+  if (h_counts) CK(cudaMemcpyAsync(h_counts, c->d_counts, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (h_status) CK(cudaMemcpyAsync(h_status, c->d_status, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (h_moves)
+    CK(cudaMemcpyAsync(h_moves, c->d_moves, N * FPC_MAX_MOVES * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  if (h_flat)
+    CK(cudaMemcpyAsync(h_flat, c->d_flat, N * FPC_MAX_MOVES * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (h_planes) CK(cudaMemcpyAsync(h_planes, d_planes, N * ssz * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (h_mask) CK(cudaMemcpyAsync(h_mask, d_mask, N * asz * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FPC_OK;
+}
+
+static int host_make(fpc_ctx *c, const uint8_t *h_in, const uint64_t *h_moves, const int32_t *h_flat, int n,
+                     uint8_t *h_out, int32_t *h_err) {
+  int rc = ctx_check(c, n, "fpc_host_make");
+  if (rc != FPC_OK) return rc;
+  if (n == 0) return FPC_OK;
+  if (!h_in || !h_out || (!h_moves && !h_flat)) return fail(FPC_ERR_ARG, "fpc_host_make: null argument");
+  const size_t N = (size_t)n;
+  CK(cudaMemcpyAsync(c->d_boards, h_in, N * c->rec, cudaMemcpyHostToDevice, c->stream));
+  if (h_moves) {
+    CK(cudaMemcpyAsync(c->d_moves, h_moves, N * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    rc = fpc_make_moves(c->R, c->d_boards, c->d_moves, n, c->d_boards2, c->d_err, c->stream);
+  } else {
+    CK(cudaMemcpyAsync(c->d_flat, h_flat, N * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    rc = fpc_make_index(c->R, c->d_boards, c->d_flat, n, c->d_boards2, c->d_err, c->stream);
+  }
+  if (rc != FPC_OK) return rc;
+  CK(cudaMemcpyAsync(h_out, c->d_boards2, N * c->rec, cudaMemcpyDeviceToHost, c->stream));
+  if (h_err) CK(cudaMemcpyAsync(h_err, c->d_err, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FPC_OK;
+}
+
+int fpc_host_make_moves(fpc_ctx *c, const uint8_t *h_in, const uint64_t *h_moves, int n, uint8_t *h_out,
+                        int32_t *h_err) {
+  return host_make(c, h_in, h_moves, nullptr, n, h_out, h_err);
+}
+int fpc_host_make_index(fpc_ctx *c, const uint8_t *h_in, const int32_t *h_flat, int n, uint8_t *h_out,
+                        int32_t *h_err) {
+  return host_make(c, h_in, nullptr, h_flat, n, h_out, h_err);
+}
+
+int fpc_host_playout_step(fpc_ctx *c, uint8_t *h_boards, int n, uint64_t seed, uint64_t *h_game, int32_t *h_ply,
+                          const uint8_t *h_start, int max_plies, uint64_t game_stride, int32_t *h_counts,
+                          int32_t *h_status, float *d_planes, int k_all, float *d_mask) {
+  int rc = ctx_check(c, n, "fpc_host_playout_step");
+  if (rc != FPC_OK) return rc;
+  if (n == 0) return FPC_OK;
+  if (!h_boards || !h_game || !h_ply || !h_start) return fail(FPC_ERR_ARG, "fpc_host_playout_step: null argument");
+  const size_t N = (size_t)n;
+  CK(cudaMemcpyAsync(c->d_boards, h_boards, N * c->rec, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_game, h_game, N * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_ply, h_ply, N * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_start, h_start, c->rec, cudaMemcpyHostToDevice, c->stream));
+  rc = fpc_playout_step(c->R, c->d_boards, n, seed, c->d_game, c->d_ply, c->d_start, max_plies, game_stride, nullptr,
+                        c->d_counts, c->d_status, d_planes, nullptr, k_all, d_mask, nullptr, c->stream);
+  if (rc != FPC_OK) return rc;
+  CK(cudaMemcpyAsync(h_boards, c->d_boards, N * c->rec, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(h_game, c->d_game, N * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(h_ply, c->d_ply, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (h_counts) CK(cudaMemcpyAsync(h_counts, c->d_counts, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (h_status) CK(cudaMemcpyAsync(h_status, c->d_status, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+Workload (configs[1]): random-playout batched env, 4096 concurrent games per GPU on the 14x14 board
+from the STANDARD start (castling rights on), 2048-ply cap, finished slots re-seeded.  One STEP = one
+pass of the hot path over the batch: for each of the 4096 resident positions, pseudo-legal movegen ->
+legal filter -> result -> f32 input planes [24,14,14] -> f32 legal-move mask [120,14,14] -> pick a
+move (deterministic splitmix) -> make-move.  That is one fused kernel launch.
+
+  value  positions/s with the board store resident in HBM (device timed, CUDA events).
+  e2e    the same step through the C-ABI host entry point fpc_host_playout_step: boards / game
+         ids / plies come from pinned HOST memory every step and go back to it; planes and masks
+         stay on the device exactly as the reference's GetEncodedStates(device="cuda") leaves them.
+
+`--impl reference` times the UNMODIFIED reference rules engine (oracle/_ref) on the host cores over
+the same workload (n slots resident as chess::Board objects, one ply per slot per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R = 14
+N_GAMES = 4096
+MAX_PLIES = 2048
+SEED = 0x5EED
+BYTES_PER_POSITION = 2 * 208 + 24 * 196 * 4 + 120 * 196 * 4  # 113,312
+METRIC = "legal positions/sec (movegen+make+encode)"
+UNIT = "positions/s"
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": "configs[1] random-playout batched env: 4096 concurrent games/GPU, 14x14 STANDARD start, "
+                    "castling on, 2048-ply cap; per position: movegen + legal filter + result + f32 planes "
+                    "[24,14,14] + f32 mask [120,14,14] + make",
+        "games_per_gpu": N_GAMES, "board": "14x14/3", "max_plies": MAX_PLIES, "seed": SEED,
+        "parallelism": f"games sharded over {n_gpus} GPU(s), no data-path collective",
+        "l2": "each step writes 464 MB of planes+mask per GPU (> 126 MB L2), so stores drain to HBM; "
+              "the 0.85 MB board store is the resident state by design",
+        "algorithmic_bytes_per_position": BYTES_PER_POSITION,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args) -> None:
+    """The reference's own CPU implementation of the path (oracle/_ref), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from alphazero_4_player_chess_b200.fen import start_record
+    from oracle import ref_engine
+    if not ref_engine.available(R):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_engine_R14.so not built"}))
+        return
+    eng = ref_engine.RefEngine(R)
+    threads = host_threads()
+    env = ref_engine.RefEnv(eng, start_record("STANDARD", castling=True), N_GAMES, SEED, n_threads=threads,
+                            max_plies=MAX_PLIES)
+    for _ in range(args.warmup):
+        env.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        env.step()
+    dt = time.perf_counter() - t0
+    env.close()
+    value = args.steps * N_GAMES / dt
+    sample = (f"{args.steps} steps x {N_GAMES} resident games through chess::Board (GetGameResult + "
+              f"GetPseudoLegalMoves2 + make/IsKingInCheck/undo + MakeMove), engine path B1: no planes/mask "
+              f"tensors are written (favours the reference)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def cpu_baseline_leg(seconds: float = 12.0) -> dict:
+    from alphazero_4_player_chess_b200.fen import start_record
+    from oracle import ref_engine
+    threads = host_threads()
+    if ref_engine.available(R):
+        eng = ref_engine.RefEngine(R)
+        env = ref_engine.RefEnv(eng, start_record("STANDARD", castling=True), N_GAMES, SEED, n_threads=threads,
+                                max_plies=MAX_PLIES)
+        env.step()
+        steps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            env.step()
+            steps += 1
+        dt = time.perf_counter() - t0
+        env.close()
+        return {"value": steps * N_GAMES / dt, "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": f"{steps} steps x {N_GAMES} games of the same workload through the unmodified reference "
+                          f"engine (oracle/_ref), {dt:.1f} s; engine path only, no planes/mask written"}
+    from oracle.port import Oracle
+    o = Oracle(R, 3)
+    t0 = time.perf_counter()
+    n, _ = o.bench_playout(start_record("STANDARD", castling=True), SEED, 0, 400000, MAX_PLIES)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n} playout positions through oracle/fpc_oracle.c, single thread, {dt:.1f} s"}
+
+
+def run_ours(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from alphazero_4_player_chess_b200 import _lib
+    from alphazero_4_player_chess_b200.env import BatchedEnv
+    from alphazero_4_player_chess_b200.fen import start_record
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    L = _lib.lib()
+    start = start_record("STANDARD", castling=True)
+    env = BatchedEnv(R, N_GAMES, device=f"cuda:{local}")
+    env.reset_playout(start, first_game=rank * N_GAMES)
+    stride = world * N_GAMES
+
+    def step():
+        env.playout_step(seed=SEED, max_plies=MAX_PLIES, game_stride=stride, planes=True, mask=True, k=-1)
+
+    # a few hundred plies in, the position mix is representative (captures, checks, promotions)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.counters.zero_()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    counters = env.counters.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)  # NCCL: statistics only
+    ms_max = float(t.item())
+    positions = int(counters[0].item())
+    assert positions == world * N_GAMES * args.steps, (positions, world, args.steps)
+    value = positions / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI, copies inside the timed region -----------------
+    ctx = L.fpc_ctx_create(local, R, N_GAMES)
+    if not ctx:
+        raise SystemExit(L.fpc_last_error().decode())
+    rec = env.geom.record_bytes
+    h_boards = torch.from_numpy(np.broadcast_to(start, (N_GAMES, rec)).copy()).pin_memory()
+    h_game = torch.arange(rank * N_GAMES, (rank + 1) * N_GAMES, dtype=torch.int64).pin_memory()
+    h_ply = torch.zeros(N_GAMES, dtype=torch.int32).pin_memory()
+    h_counts = torch.zeros(N_GAMES, dtype=torch.int32).pin_memory()
+    h_status = torch.zeros(N_GAMES, dtype=torch.int32).pin_memory()
+    h_start = torch.from_numpy(start.copy()).pin_memory()
+    d_planes, d_mask = env.planes_buffer(), env.mask_buffer()
+
+    def e2e_step():
+        _lib.check(L.fpc_host_playout_step(ctx, h_boards.data_ptr(), N_GAMES, SEED, h_game.data_ptr(),
+                                           h_ply.data_ptr(), h_start.data_ptr(), MAX_PLIES, stride,
+                                           h_counts.data_ptr(), h_status.data_ptr(), d_planes.data_ptr(), -1,
+                                           d_mask.data_ptr()))
+
+    e2e_steps = args.steps
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    legal_seen = 0
+    for _ in range(e2e_steps):
+        e2e_step()  # synchronous: returns after the D2H copies have landed
+        legal_seen += int(h_counts[0])
+    dt = time.perf_counter() - t0
+    barrier()
+    L.fpc_ctx_destroy(ctx)
+    t2 = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_GAMES * e2e_steps / float(t2.item())
+    h2d = N_GAMES * (rec + 8 + 4) + rec
+    d2h = N_GAMES * (rec + 8 + 4 + 4 + 4)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        per_gpu_ms = ms_max / args.steps  # one observe_kernel launch per step per GPU
+        achieved = N_GAMES * BYTES_PER_POSITION / (per_gpu_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("observe_kernel")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "fpc_host_playout_step: boards/game ids/plies from pinned host memory and back every "
+                            "step; planes+mask left on the device as the reference's device='cuda' does"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "observe_kernel<Geo<14,3>>",
+                         "bytes_per_launch": N_GAMES * BYTES_PER_POSITION},
+            "clocks": clocks,
+            "stats": {"positions": positions, "finished_games": int(counters[1].item()),
+                      "avg_legal_moves": float(counters[6].item()) / max(positions, 1),
+                      "move_buffer_overflows": int(counters[7].item())},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_leg()
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+/* fpc.h -- C-ABI of the B200-native batched four-player-chess environment.
+ *
+ * This is the drop-in boundary underneath the reference's pybind11 module `alphazero_cpp`
+ * (/root/reference/src/cpp/wrapper.cpp:15-254).  Every entry point names the reference
+ * interface it replaces.  Plain pointers and sizes only; no torch types; no exceptions cross
+ * this ABI: functions return FPC_OK or a negative code and fpc_last_error() holds the text
+ * (the binding turns codes into RuntimeError, wrapper.cpp:17-27).
+ *
+ * All `d_` pointers are DEVICE pointers on the current CUDA device; `h_` pointers are HOST
+ * pointers.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls
+ * taking a stream are asynchronous with respect to the host.  There is NO CPU fallback: with no
+ * usable CUDA device every compute entry point fails with FPC_ERR_CUDA.
+ *
+ * Geometry.  The reference fixes the board at compile time (engine/board.h:22-24).  Here the
+ * side length R selects a compiled instantiation: R=14 (invalid_area 3, the 4pchess board of
+ * BASELINE.json), R=8 (invalid_area 2, the reference as checked in), R=10 (2), R=13 (3).
+ *
+ * Board record (one game), fpc_record_bytes(R) bytes, 16-byte aligned in arrays:
+ *   [0, R*R)      piece bytes, row-major, the reference's Piece bits (engine/board.h:101-104):
+ *                 present<<7 | color<<5 | type<<2; empty = 0x18
+ *   [R*R]         side to move (0 RED, 1 BLUE, 2 YELLOW, 3 GREEN)
+ *   [R*R+1, +5)   castling rights per colour (engine/board.h:290-291): 0x80 | ks<<6 | qs<<5
+ *   [R*R+5, +9)   king square per colour (row*R+col; R*R = captured).  Output only: kernels
+ *                 recompute it from the squares.
+ *   rest          zero padding.   R=14: 208 B, R=8: 80 B.
+ *
+ * Move: the reference's 8-byte chess::Move image (engine/board.h:419-435) as a little-endian
+ * uint64: byte0 from, byte1 to, byte2 captured Piece bits (0x18 none), byte3 promotion type
+ * (6 none), byte4/5 rook from/to (R*R none), byte6 rights before, byte7 rights after (0 absent).
+ *
+ * Canonical move order.  The reference's move order depends on call history;
+ * every list returned here is sorted by (flat action index, promotion type).
+ */
+#ifndef FPC_H_
+#define FPC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPC_MAX_MOVES 300 /* engine/board.h:706 move_buffer_size_ */
+#define FPC_NUM_STATE_CHANNELS 24 /* src/cpp/board.h:21 */
+
+#define FPC_OK 0
+#define FPC_ERR_ARG (-1)      /* bad argument (unsupported R, null pointer, negative n) */
+#define FPC_ERR_CUDA (-2)     /* CUDA runtime error, or no device */
+#define FPC_ERR_MOVE (-3)     /* "piece missing for move" (engine/board.cpp:1046-1054) */
+#define FPC_ERR_OVERFLOW (-4) /* more than FPC_MAX_MOVES pseudo-legal moves (reference aborts) */
+
+/* status word written per game by fpc_observe / fpc_playout_step */
+#define FPC_STATUS_RESULT_MASK 0x3     /* GameResult: 0 IN_PROGRESS 1 WIN_RY 2 WIN_BG 3 STALEMATE */
+#define FPC_STATUS_IN_CHECK 0x100      /* side to move is in check (set only when it has no legal move) */
+#define FPC_STATUS_CAN_TAKE_KING 0x200 /* some legal move captures a king */
+#define FPC_STATUS_OVERFLOW 0x400      /* move buffer overflow */
+#define FPC_STATUS_FINISHED 0x800      /* playout only: the game in this slot ended and was re-seeded */
+
+const char *fpc_last_error(void);
+int fpc_version(void);
+
+/* statics of fpchess::Board (src/cpp/board.cpp:9-14, wrapper.cpp:175-180) */
+int fpc_supported(int R);           /* 1 if R is a compiled geometry */
+int fpc_invalid_area(int R);        /* Board::invalidArea */
+int fpc_record_bytes(int R);
+int fpc_num_action_channels(int R); /* Board::num_action_channels = 8R+8 */
+int fpc_action_space_size(int R);   /* Board::action_space_size */
+int fpc_state_space_size(int R);    /* Board::state_space_size = 24*R*R */
+
+/* fpchess::Move index map (src/cpp/move.cpp:23-104): host-side, no device needed. */
+uint64_t fpc_move_from_flat(int R, int flat_index); /* Move(int flat_index), move.cpp:41-61 */
+int fpc_move_flat_index(int R, uint64_t move);      /* Move::GetFlatIndex, -1 where GetIndex throws */
+
+/* ---- device-pointer batch operations ------------------------------------------------------ */
+
+/* The fused observation kernel.  For each of n board records:
+ *   legal moves      = fpchess::Board::GetLegalMoves (src/cpp/board.cpp:94-118) over
+ *                      chess::Board::GetPseudoLegalMoves2 (engine/board.cpp:846-889)
+ *   status           = chess::Board::GetGameResult (engine/board.cpp:891-939), order-independent
+ *                      contract, plus the FPC_STATUS_* flags
+ *   planes           = Board::GetEncodedStates (src/cpp/board.cpp:305-356): [n][24][R][R] f32,
+ *                      rotated by k quarter turns (d_k[g] if d_k != NULL, else k_all; k_all = -1
+ *                      means "each game by its own side to move")
+ *   mask             = FourPlayerChess.get_legal_moves_mask
+ *                      (src/py/four_player_chess_board.py:36-55): [n][8R+8][R][R] f32, unrotated
+ *   flat indices     = Board::GetLegalMovesIndices (src/cpp/board.cpp:424-449) as flat indices
+ * Any output pointer may be NULL.  d_moves / d_flat are [n][FPC_MAX_MOVES]. */
+int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_t *d_flat, int32_t *d_counts,
+                int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all, float *d_mask, void *stream);
+
+/* Board::GetEncodedStates alone (no move generation). */
+int fpc_encode(int R, const uint8_t *d_boards, int n, const int32_t *d_k, int k_all, float *d_planes,
+               void *stream);
+
+/* chess::Board::MakeMove (engine/board.cpp:1028-1096) with full generator moves, as used by
+ * Board::TakeAction (src/cpp/board.cpp:234-239).  d_err[g] = FPC_OK or FPC_ERR_MOVE.
+ * d_in == d_out is allowed. */
+int fpc_make_moves(int R, const uint8_t *d_in, const uint64_t *d_moves, int n, uint8_t *d_out, int32_t *d_err,
+                   void *stream);
+
+/* MakeMove with index-built moves Move(flat_index) (src/cpp/move.cpp:41-61) -- the self-play
+ * path (src/cpp/node.cpp:87-92, src/py/alphazero.py:119-121): only from/to, so no promotion,
+ * no rook move, no rights update. */
+int fpc_make_index(int R, const uint8_t *d_in, const int32_t *d_flat, int n, uint8_t *d_out, int32_t *d_err,
+                   void *stream);
+
+/* chess::Board::CalculateHeuristic (engine/board.cpp:1263-1292) for the team to move. */
+int fpc_heuristic(int R, const uint8_t *d_boards, int n, int32_t *d_value, void *stream);
+
+/* One ply of the deterministic random playout for every game slot (BASELINE.json configs[1]):
+ * observe the position (planes/mask optional, as fpc_observe), then either finish the game
+ * (result != IN_PROGRESS, or d_ply[g]+1 == max_plies) and re-seed the slot from h/d start
+ * record with game id += game_stride, or play
+ * legal[ ((mix(seed, game, ply) >> 32) * n_legal) >> 32 ] with MakeMove(full).
+ * d_boards is updated in place.  d_counters (8 x uint64, may be NULL) accumulates:
+ * [0] positions, [1] finished games, [2..5] result histogram of finished games (index =
+ * GameResult, 0 = ply cap), [6] sum of n_legal, [7] overflow count. */
+int fpc_playout_step(int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d_game, int32_t *d_ply,
+                     const uint8_t *d_start, int max_plies, uint64_t game_stride, uint64_t *d_chosen,
+                     int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all,
+                     float *d_mask, uint64_t *d_counters, void *stream);
+
+/* ---- host-buffer operations (per-object calls of the binding; e2e measurement) ------------- */
+
+typedef struct fpc_ctx fpc_ctx;
+
+/* One context per (device, R): a stream plus pinned staging and device buffers for up to
+ * max_n boards.  Not thread-safe; one per host thread. */
+fpc_ctx *fpc_ctx_create(int device, int R, int max_n);
+void fpc_ctx_destroy(fpc_ctx *ctx);
+void *fpc_ctx_stream(fpc_ctx *ctx);
+
+/* Host in, host out.  Any output may be NULL.  h_planes / h_mask are host buffers; when the
+ * caller wants the tensors left on the device (the reference's device="cuda"), it passes
+ * d_planes / d_mask (device pointers) instead and NULL for the host ones. */
+int fpc_host_observe(fpc_ctx *ctx, const uint8_t *h_boards, int n, uint64_t *h_moves, int32_t *h_flat,
+                     int32_t *h_counts, int32_t *h_status, float *h_planes, float *d_planes, int k_all,
+                     float *h_mask, float *d_mask);
+int fpc_host_make_moves(fpc_ctx *ctx, const uint8_t *h_in, const uint64_t *h_moves, int n, uint8_t *h_out,
+                        int32_t *h_err);
+int fpc_host_make_index(fpc_ctx *ctx, const uint8_t *h_in, const int32_t *h_flat, int n, uint8_t *h_out,
+                        int32_t *h_err);
+/* One playout ply through host buffers: boards, game ids and plies are copied in, stepped and
+ * copied back; planes/mask stay on the device (d_planes/d_mask may be NULL). */
+int fpc_host_playout_step(fpc_ctx *ctx, uint8_t *h_boards, int n, uint64_t seed, uint64_t *h_game,
+                          int32_t *h_ply, const uint8_t *h_start, int max_plies, uint64_t game_stride,
+                          int32_t *h_counts, int32_t *h_status, float *d_planes, int k_all, float *d_mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPC_H_ */

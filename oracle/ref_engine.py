@@ -45,6 +45,12 @@ class RefEngine:
         lib.ref_bench_playout.argtypes = [_u8p, C.c_uint64, C.c_int, C.c_uint64, C.c_int,
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.ref_bench_playout.restype = C.c_double
+        lib.ref_env_create.argtypes = [_u8p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
+        lib.ref_env_create.restype = C.c_void_p
+        lib.ref_env_step.argtypes = [C.c_void_p]
+        lib.ref_env_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
+        lib.ref_env_get.argtypes = [C.c_void_p, C.c_int, _u8p, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        lib.ref_env_destroy.argtypes = [C.c_void_p]
         self.R = lib.ref_rows()
         self.IA = lib.ref_invalid_area()
         self.record_bytes = lib.ref_record_bytes()
@@ -117,3 +123,36 @@ class RefEngine:
         rate = self.lib.ref_bench_playout(np.ascontiguousarray(start), seed, n_threads,
                                           min_positions, max_plies, C.byref(pos), C.byref(chk))
         return dict(positions_per_s=rate, positions=pos.value, checksum=chk.value)
+
+
+class RefEnv:
+    """configs[1] on the host: n_slots games resident as reference Board objects, one ply per step."""
+
+    def __init__(self, engine: RefEngine, start, n_slots, seed, first_game=0, stride=None, max_plies=2048,
+                 n_threads=1):
+        self.e = engine
+        self.n = n_slots
+        self.h = engine.lib.ref_env_create(np.ascontiguousarray(start), n_slots, seed, first_game,
+                                           n_slots if stride is None else stride, max_plies, n_threads)
+
+    def step(self):
+        self.e.lib.ref_env_step(self.h)
+
+    def stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.e.lib.ref_env_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return dict(positions=a.value, finished=b.value, sum_legal=c.value)
+
+    def get(self, slot):
+        rec = np.zeros(self.e.record_bytes, dtype=np.uint8)
+        g, p = C.c_uint64(), C.c_int()
+        self.e.lib.ref_env_get(self.h, slot, rec, C.byref(g), C.byref(p))
+        return rec, g.value, p.value
+
+    def close(self):
+        if self.h:
+            self.e.lib.ref_env_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()

@@ -18,6 +18,9 @@
 // links or loads it.
 
 #include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -325,6 +328,127 @@ double ref_bench_playout(const uint8_t *start, uint64_t seed, int n_threads, uin
   if (positions_out) *positions_out = positions.load();
   if (checksum_out) *checksum_out = checksum.load();
   return static_cast<double>(positions.load()) / dt;
+}
+
+// ---- the configs[1] workload on the host: n_slots concurrent games resident as chess::Board
+// objects, one ply per slot per step, finished slots re-seeded exactly like fpc_playout_step.
+// A persistent pool of n_threads workers splits the slots (CPU baseline B1).
+struct RefEnv {
+  std::vector<std::unique_ptr<Board>> boards;
+  std::vector<uint64_t> game;
+  std::vector<int> ply;
+  std::vector<uint8_t> start;
+  uint64_t seed = 0, stride = 0;
+  int max_plies = 0, n_threads = 1;
+  std::atomic<uint64_t> positions{0}, finished{0}, sum_legal{0};
+  // pool
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  uint64_t epoch = 0;
+  int pending = 0;
+  bool quit = false;
+
+  void StepSlice(int t) {
+    chess::Move legal[300];
+    const int n = static_cast<int>(boards.size());
+    const int lo = static_cast<int>(static_cast<int64_t>(n) * t / n_threads);
+    const int hi = static_cast<int>(static_cast<int64_t>(n) * (t + 1) / n_threads);
+    uint64_t fin = 0, sl = 0;
+    for (int i = lo; i < hi; ++i) {
+      Board &b = *boards[i];
+      int res_ref = static_cast<int>(b.GetGameResult());
+      (void)res_ref;
+      size_t k = LegalMoves(b, legal);
+      int res = CanonicalResult(b, k);
+      sl += k;
+      bool done = res != 0;
+      if (!done) {
+        SortCanonical(legal, k);
+        b.MakeMove(legal[Pick(seed, game[i], static_cast<uint64_t>(ply[i]), static_cast<uint32_t>(k))]);
+        done = ply[i] + 1 >= max_plies;
+      }
+      if (done) {
+        ++fin;
+        boards[i] = std::make_unique<Board>(BoardFromRecord(start.data()));
+        game[i] += stride;
+        ply[i] = 0;
+      } else {
+        ++ply[i];
+      }
+    }
+    positions.fetch_add(static_cast<uint64_t>(hi - lo));
+    finished.fetch_add(fin);
+    sum_legal.fetch_add(sl);
+  }
+
+  void Worker(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_go.wait(lk, [&] { return quit || epoch != seen; });
+        if (quit) return;
+        seen = epoch;
+      }
+      StepSlice(t);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (--pending == 0) cv_done.notify_one();
+      }
+    }
+  }
+};
+
+void *ref_env_create(const uint8_t *start, int n_slots, uint64_t seed, uint64_t first_game, uint64_t stride,
+                     int max_plies, int n_threads) {
+  RefEnv *e = new RefEnv();
+  e->start.assign(start, start + REC);
+  e->seed = seed;
+  e->stride = stride;
+  e->max_plies = max_plies;
+  e->n_threads = n_threads < 1 ? 1 : n_threads;
+  for (int i = 0; i < n_slots; ++i) {
+    e->boards.push_back(std::make_unique<Board>(BoardFromRecord(start)));
+    e->game.push_back(first_game + static_cast<uint64_t>(i));
+    e->ply.push_back(0);
+  }
+  for (int t = 0; t < e->n_threads; ++t) e->workers.emplace_back([e, t] { e->Worker(t); });
+  return e;
+}
+
+void ref_env_step(void *env) {
+  RefEnv *e = static_cast<RefEnv *>(env);
+  std::unique_lock<std::mutex> lk(e->mu);
+  e->pending = e->n_threads;
+  ++e->epoch;
+  e->cv_go.notify_all();
+  e->cv_done.wait(lk, [&] { return e->pending == 0; });
+}
+
+void ref_env_stats(void *env, uint64_t *positions, uint64_t *finished, uint64_t *sum_legal) {
+  RefEnv *e = static_cast<RefEnv *>(env);
+  *positions = e->positions.load();
+  *finished = e->finished.load();
+  *sum_legal = e->sum_legal.load();
+}
+
+void ref_env_get(void *env, int slot, uint8_t *rec, uint64_t *game, int *ply) {
+  RefEnv *e = static_cast<RefEnv *>(env);
+  RecordFromBoard(*e->boards[slot], rec);
+  *game = e->game[slot];
+  *ply = e->ply[slot];
+}
+
+void ref_env_destroy(void *env) {
+  RefEnv *e = static_cast<RefEnv *>(env);
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->quit = true;
+  }
+  e->cv_go.notify_all();
+  for (auto &w : e->workers) w.join();
+  delete e;
 }
 
 }  // extern "C"

@@ -1,0 +1,310 @@
+"""-m gpu: the CUDA path (through the C-ABI of include/fpc.h) against the oracle, bit-exact.
+
+Integer/byte/index work: equality.  The f32 planes and masks hold only 0.0 / 1.0, so they are
+compared with exact equality too (tolerance 0)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from alphazero_4_player_chess_b200 import _lib
+from alphazero_4_player_chess_b200.env import BatchedEnv
+from alphazero_4_player_chess_b200.fen import START_FENS, start_record
+from alphazero_4_player_chess_b200.geometry import GEOMETRIES
+from tests.util import SEED, mixed_positions, oracle_for
+
+pytestmark = pytest.mark.gpu
+
+PERFT = {  # SURVEY 8c known answers, reproduced by oracle/_ref in tests/test_oracle_vs_ref.py
+    "STANDARD": [20, 395, 7800, 152050, 3450730],
+    "EIGHT_SIMPLE": [14, 66, 887, 4086, 58416, 258524],
+    "EIGHT": [10, 83, 677, 4828, 41693],
+    "TEN": [14, 215, 2856, 41416],
+}
+
+
+def gpu_perft(name, depth, castling):
+    _, R = START_FENS[name]
+    L = _lib.lib()
+    frontier = torch.as_tensor(start_record(name, castling=castling)).cuda().unsqueeze(0).contiguous()
+    out = []
+    for d in range(depth):
+        n = frontier.shape[0]
+        counts = torch.zeros(n, dtype=torch.int32, device="cuda")
+        moves = torch.zeros((n, _lib.FPC_MAX_MOVES), dtype=torch.int64, device="cuda")
+        _lib.check(L.fpc_observe(R, frontier.data_ptr(), n, moves.data_ptr(), None, counts.data_ptr(), None,
+                                 None, None, -1, None, None))
+        out.append(int(counts.sum().item()))
+        if d == depth - 1:
+            break
+        idx = torch.repeat_interleave(torch.arange(n, device="cuda"), counts.long())
+        start = torch.cumsum(counts.long(), 0) - counts.long()
+        within = torch.arange(idx.numel(), device="cuda") - start[idx]
+        mv = moves[idx, within].contiguous()
+        parents = frontier[idx].contiguous()
+        children = torch.empty_like(parents)
+        err = torch.zeros(idx.numel(), dtype=torch.int32, device="cuda")
+        _lib.check(L.fpc_make_moves(R, parents.data_ptr(), mv.data_ptr(), idx.numel(), children.data_ptr(),
+                                    err.data_ptr(), None))
+        assert int(err.abs().sum().item()) == 0
+        frontier = children
+    return out
+
+
+@pytest.mark.parametrize("name", list(PERFT))
+@pytest.mark.parametrize("castling", [False, True])
+def test_perft_known_answers(name, castling):
+    want = PERFT[name]
+    depth = len(want) if name != "STANDARD" else 5
+    assert gpu_perft(name, depth, castling) == want[:depth]
+
+
+@pytest.mark.parametrize("name,n", [("STANDARD", 16384), ("EIGHT_SIMPLE", 4096), ("EIGHT", 2048), ("TEN", 4096),
+                                    ("THIRTEEN", 2048)])
+def test_observe_matches_oracle(name, n):
+    """configs[2]: legal lists, results, planes and masks for synthetic playout positions."""
+    _, R = START_FENS[name]
+    g = GEOMETRIES[R]
+    o = oracle_for(R)
+    recs = mixed_positions(name, n)
+    n = recs.shape[0]
+    env = BatchedEnv(R, n)
+    env.load(recs)
+    env.observe(planes=True, mask=True, moves=True, flat=True, k=-1)
+    torch.cuda.synchronize()
+    counts = env.counts.cpu().numpy()
+    status = env.status.cpu().numpy()
+    moves = env.moves_buffer().cpu().numpy().view(np.uint64)
+    flat = env.flat_buffer().cpu().numpy()
+    for i in range(n):
+        want = o.legal_moves(recs[i])
+        assert counts[i] == len(want), i
+        assert (moves[i, : len(want)] == want).all(), i
+        assert [o.move_flat_index(m) for m in want] == flat[i, : len(want)].tolist(), i
+        res, nl, kc = o.game_result(recs[i])
+        assert (status[i] & 3) == res and bool(status[i] & _lib.STATUS_CAN_TAKE_KING) == kc, i
+        assert not (status[i] & _lib.STATUS_OVERFLOW)
+    # dense outputs, chunked (the f32 mask is 94 KB per position at 14x14)
+    turns = recs[:, g.off_turn].astype(np.int32)
+    planes = env.planes_buffer()
+    mask = env.mask_buffer()
+    for lo in range(0, n, 1024):
+        hi = min(n, lo + 1024)
+        assert np.array_equal(planes[lo:hi].cpu().numpy(), o.encode(recs[lo:hi], turns[lo:hi]))
+        assert np.array_equal(mask[lo:hi].cpu().numpy(), o.mask(recs[lo:hi]))
+    # the reference rotates a whole batch by the colour of states[0]: fixed k, and a k tensor
+    for k in range(4):
+        got = env.encode(k=k)[:512].cpu().numpy()
+        assert np.array_equal(got, o.encode(recs[:512], k))
+    kt = torch.arange(n, dtype=torch.int32, device="cuda") % 4
+    got = env.encode(k=kt)[:512].cpu().numpy()
+    assert np.array_equal(got, o.encode(recs[:512], kt[:512].cpu().numpy()))
+
+
+@pytest.mark.parametrize("name", ["STANDARD", "EIGHT_SIMPLE", "TEN"])
+def test_make_full_and_index_match_oracle(name):
+    _, R = START_FENS[name]
+    o = oracle_for(R)
+    L = _lib.lib()
+    recs = mixed_positions(name, 600)[::3]
+    parents, full, idx = [], [], []
+    for r in recs:
+        for m in o.legal_moves(r):
+            parents.append(r)
+            full.append(m)
+            idx.append(o.move_flat_index(m))
+    parents = np.stack(parents)
+    n = len(full)
+    d_par = torch.as_tensor(parents).cuda()
+    d_mv = torch.as_tensor(np.array(full, dtype=np.uint64).view(np.int64)).cuda()
+    d_ix = torch.as_tensor(np.array(idx, dtype=np.int32)).cuda()
+    out = torch.empty_like(d_par)
+    err = torch.zeros(n, dtype=torch.int32, device="cuda")
+    _lib.check(L.fpc_make_moves(R, d_par.data_ptr(), d_mv.data_ptr(), n, out.data_ptr(), err.data_ptr(), None))
+    got = out.cpu().numpy()
+    assert int(err.abs().sum().item()) == 0
+    for i in range(n):
+        assert np.array_equal(got[i], o.make_move(parents[i], full[i])), i
+    _lib.check(L.fpc_make_index(R, d_par.data_ptr(), d_ix.data_ptr(), n, out.data_ptr(), err.data_ptr(), None))
+    got = out.cpu().numpy()
+    assert int(err.abs().sum().item()) == 0
+    for i in range(n):
+        assert np.array_equal(got[i], o.make_index(parents[i], idx[i])), i
+
+
+def test_make_missing_piece_reports_error():
+    R = 14
+    g = GEOMETRIES[R]
+    L = _lib.lib()
+    rec = start_record("STANDARD")
+    empty_sq = 6 * R + 6
+    mv = np.array([empty_sq | ((empty_sq + 1) << 8) | (0x18 << 16) | (6 << 24) | (g.nsq << 32) | (g.nsq << 40)],
+                  dtype=np.uint64)
+    d_in = torch.as_tensor(rec).cuda().unsqueeze(0).contiguous()
+    d_mv = torch.as_tensor(mv.view(np.int64)).cuda()
+    out = torch.empty_like(d_in)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(L.fpc_make_moves(R, d_in.data_ptr(), d_mv.data_ptr(), 1, out.data_ptr(), err.data_ptr(), None))
+    assert err.item() == _lib.FPC_ERR_MOVE  # "piece missing for move" engine/board.cpp:1046-1054
+
+
+@pytest.mark.parametrize("name,n_games,steps", [("STANDARD", 512, 260), ("EIGHT_SIMPLE", 256, 200), ("TEN", 128, 200)])
+@pytest.mark.parametrize("castling", [True, False])
+def test_playout_replays_oracle_games(name, n_games, steps, castling):
+    """configs[1]: the fused playout kernel plays the very games the oracle plays."""
+    _, R = START_FENS[name]
+    o = oracle_for(R)
+    start = start_record(name, castling=castling)
+    max_plies = 120
+    env = BatchedEnv(R, n_games)
+    env.reset_playout(start)
+    boards, counts, status, chosen, games, plies = [], [], [], [], [], []
+    for _ in range(steps):
+        games.append(env.game.cpu().numpy().copy())
+        plies.append(env.ply.cpu().numpy().copy())
+        boards.append(env.boards.cpu().numpy().copy())
+        env.playout_step(seed=SEED, max_plies=max_plies, planes=False, mask=False, chosen=True)
+        counts.append(env.counts.cpu().numpy().copy())
+        status.append(env.status.cpu().numpy().copy())
+        chosen.append(env.chosen.cpu().numpy().view(np.uint64).copy())
+    total = 0
+    for slot in range(0, n_games, 7):
+        cache = {}
+        for t in range(steps):
+            gid, ply = int(games[t][slot]), int(plies[t][slot])
+            if gid not in cache:
+                cache[gid] = o.playout(start, SEED, gid, max_plies)
+            p = cache[gid]
+            assert ply < p["n"], (slot, t, gid, ply)
+            assert np.array_equal(boards[t][slot], p["recs"][ply]), (slot, t)
+            assert counts[t][slot] == p["n_legal"][ply]
+            assert (status[t][slot] & 3) == p["result"][ply]
+            assert chosen[t][slot] == p["moves"][ply]
+            finished = p["result"][ply] != 0 or ply + 1 >= max_plies
+            assert bool(status[t][slot] & _lib.STATUS_FINISHED) == finished
+            total += 1
+    assert int(env.counters[0].item()) == n_games * steps
+    assert int(env.counters[6].item()) == int(np.sum(counts))
+    assert total > 0
+
+
+def test_host_api_matches_device_api():
+    R = 14
+    L = _lib.lib()
+    o = oracle_for(R)
+    recs = mixed_positions("STANDARD", 1000)
+    n = recs.shape[0]
+    ctx = L.fpc_ctx_create(0, R, n)
+    assert ctx, L.fpc_last_error()
+    try:
+        moves = np.zeros((n, 300), dtype=np.uint64)
+        flat = np.zeros((n, 300), dtype=np.int32)
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        planes = np.zeros((n, 24, R, R), dtype=np.float32)
+        mask = np.zeros((n, 8 * R + 8, R, R), dtype=np.float32)
+        _lib.check(L.fpc_host_observe(ctx, recs.ctypes.data, n, moves.ctypes.data, flat.ctypes.data,
+                                      counts.ctypes.data, status.ctypes.data, planes.ctypes.data, None, -1,
+                                      mask.ctypes.data, None))
+        for i in range(n):
+            want = o.legal_moves(recs[i])
+            assert counts[i] == len(want) and (moves[i, : len(want)] == want).all()
+        turns = recs[:, GEOMETRIES[R].off_turn].astype(np.int32)
+        assert np.array_equal(planes, o.encode(recs, turns))
+        assert np.array_equal(mask, o.mask(recs))
+        # make through host buffers: first legal move of every position that has one
+        has = counts > 0
+        par = np.ascontiguousarray(recs[has])
+        mv = np.ascontiguousarray(moves[has, 0])
+        out = np.zeros_like(par)
+        err = np.zeros(len(par), dtype=np.int32)
+        _lib.check(L.fpc_host_make_moves(ctx, par.ctypes.data, mv.ctypes.data, len(par), out.ctypes.data,
+                                         err.ctypes.data))
+        assert not err.any()
+        for i in range(len(par)):
+            assert np.array_equal(out[i], o.make_move(par[i], mv[i]))
+        ix = np.ascontiguousarray(flat[has, 0])
+        _lib.check(L.fpc_host_make_index(ctx, par.ctypes.data, ix.ctypes.data, len(par), out.ctypes.data,
+                                         err.ctypes.data))
+        for i in range(len(par)):
+            assert np.array_equal(out[i], o.make_index(par[i], ix[i]))
+    finally:
+        L.fpc_ctx_destroy(ctx)
+
+
+def test_edge_cases_empty_ragged_terminal():
+    R = 14
+    g = GEOMETRIES[R]
+    L = _lib.lib()
+    o = oracle_for(R)
+    # n = 0 is a no-op
+    _lib.check(L.fpc_observe(R, None, 0, None, None, None, None, None, None, -1, None, None))
+    # unsupported geometry
+    assert L.fpc_observe(12, None, 0, None, None, None, None, None, None, -1, None, None) == _lib.FPC_ERR_ARG
+    recs = []
+    # (a) mover has no king -> other team wins, no moves (engine/board.cpp:852-856, 895-899)
+    r = start_record("STANDARD")
+    r[13 * R + 7] = 0x18
+    r[g.off_king + 0] = g.nsq
+    recs.append(r)
+    # (b) bare kings: legal moves only for the king
+    r = g.empty_record()
+    for color, sq in enumerate([13 * R + 7, 7 * R + 0, 0 * R + 6, 6 * R + 13]):
+        r[sq] = 0x80 | (color << 5) | (5 << 2)
+        r[g.off_king + color] = sq
+    recs.append(r)
+    # (c) stalemate: red king boxed in by its own pawns' blockers, not attacked
+    r = g.empty_record()
+    r[13 * R + 3] = 0x80 | (0 << 5) | (5 << 2)      # red king in the corner of its back rank
+    r[12 * R + 3] = 0x80 | (1 << 5) | (3 << 2)      # blue rook guards... placed so king cannot move
+    r[11 * R + 4] = 0x80 | (3 << 5) | (4 << 2)      # green queen covers the rest
+    r[0 * R + 6] = 0x80 | (2 << 5) | (5 << 2)
+    r[7 * R + 0] = 0x80 | (1 << 5) | (5 << 2)
+    r[6 * R + 13] = 0x80 | (3 << 5) | (5 << 2)
+    recs.append(r)
+    # (d) empty board, every colour to move
+    for t in range(4):
+        r = g.empty_record()
+        r[g.off_turn] = t
+        recs.append(r)
+    recs = np.stack(recs)
+    n = recs.shape[0]  # 7: not a multiple of the 4 warps per block
+    env = BatchedEnv(R, n)
+    env.load(recs)
+    env.observe(planes=True, mask=True, moves=True)
+    torch.cuda.synchronize()
+    counts, status = env.counts.cpu().numpy(), env.status.cpu().numpy()
+    moves = env.moves_buffer().cpu().numpy().view(np.uint64)
+    for i in range(n):
+        want = o.legal_moves(recs[i])
+        res, nl, kc = o.game_result(recs[i])
+        assert counts[i] == len(want) and (moves[i, : len(want)] == want).all(), i
+        assert (status[i] & 3) == res, i
+    assert np.array_equal(env.mask_buffer().cpu().numpy(), o.mask(recs))
+    assert np.array_equal(env.planes_buffer().cpu().numpy(), o.encode(recs, recs[:, g.off_turn].astype(np.int32)))
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] size: 4096 games; size-independent invariants of the fused step."""
+    R, n = 14, 4096
+    g = GEOMETRIES[R]
+    env = BatchedEnv(R, n)
+    env.reset_playout(start_record("STANDARD", castling=True))
+    for step in range(64):
+        before = env.boards.clone()
+        env.playout_step(seed=SEED, max_plies=2048, planes=True, mask=True)
+        if step % 16 == 15:
+            planes, mask = env.planes_buffer(), env.mask_buffer()
+            pieces = (before[:, : g.nsq] >= 0x80).sum(dim=1)
+            assert torch.equal(planes.sum(dim=(1, 2, 3)).long(), pieces.long())
+            assert bool(((planes == 0) | (planes == 1)).all()) and bool(((mask == 0) | (mask == 1)).all())
+            # distinct (plane, from) pairs <= legal moves (promotions share an index)
+            nz = mask.sum(dim=(1, 2, 3)).long()
+            assert bool((nz <= env.counts.long()).all()) and bool((nz * 4 >= env.counts.long()).all())
+            # the mask only fires on squares holding a piece of the side to move
+            turn = before[:, g.off_turn].long()
+            sq = before[:, : g.nsq].long()
+            own = ((sq >= 0x80) & (((sq >> 5) & 3) == turn[:, None])).view(n, 1, R, R)
+            assert bool((mask.amax(dim=1, keepdim=True) <= own.float()).all())
+    assert int(env.counters[0].item()) == 64 * n
