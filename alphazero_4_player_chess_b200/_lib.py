@@ -14,6 +14,7 @@ FPC_MAX_MOVES = 300
 FPC_OK, FPC_ERR_ARG, FPC_ERR_CUDA, FPC_ERR_MOVE, FPC_ERR_OVERFLOW = 0, -1, -2, -3, -4
 STATUS_RESULT_MASK, STATUS_IN_CHECK, STATUS_CAN_TAKE_KING = 0x3, 0x100, 0x200
 STATUS_OVERFLOW, STATUS_FINISHED = 0x400, 0x800
+FLAG_ASYNC_DENSE = 1
 
 _vp, _i, _u64 = C.c_void_p, C.c_int, C.c_uint64
 
@@ -29,13 +30,14 @@ SIGNATURES = {
     "fpc_state_space_size": (_i, [_i]),
     "fpc_move_from_flat": (_u64, [_i, _i]),
     "fpc_move_flat_index": (_i, [_i, _u64]),
-    "fpc_observe": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
-    "fpc_encode": (_i, [_i, _vp, _i, _vp, _i, _vp, _vp]),
+    "fpc_observe": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "fpc_join": (_i, [_vp]),
+    "fpc_encode": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "fpc_make_moves": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp]),
     "fpc_make_index": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp]),
     "fpc_heuristic": (_i, [_i, _vp, _i, _vp, _vp]),
     "fpc_playout_step": (_i, [_i, _vp, _i, _u64, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _vp, _vp, _i, _vp,
-                              _vp, _vp]),
+                              _vp, _i, _vp]),
     "fpc_ctx_create": (_vp, [_i, _i, _i]),
     "fpc_ctx_destroy": (None, [_vp]),
     "fpc_ctx_stream": (_vp, [_vp]),

@@ -5,15 +5,16 @@
 #include <stdio.h>
 #include <string.h>
 
-#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/fpc.h"
 #include "fpc_device.cuh"
 
 namespace fpc {
 
-constexpr int WARPS_PER_BLOCK = 4;
+constexpr int WARPS_PER_BLOCK = 4;  // one warp per game
+constexpr int BLOCK_THREADS = WARPS_PER_BLOCK * 32;
 
 struct ObserveParams {
   const uint8_t *boards_in;  // [n][REC]
@@ -24,10 +25,10 @@ struct ObserveParams {
   int32_t *flat;        // [n][MAX_MOVES] or null
   int32_t *counts;      // [n] or null
   int32_t *status;      // [n] or null
-  float *planes;        // [n][24][R][R] or null
+  uint32_t *plane_bits; // [n][PLANE_WORDS] or null: input planes, 1 bit per cell
   const int32_t *k;     // [n] or null
   int k_all;            // -1: own turn
-  float *mask;          // [n][A][R][R] or null
+  uint32_t *mask_bits;  // [n][MASK_WORDS] or null: legal-move mask, 1 bit per action
   // playout
   int playout;
   uint64_t seed;
@@ -39,6 +40,19 @@ struct ObserveParams {
   uint64_t *chosen;
   unsigned long long *counters;
 };
+
+// Dense outputs.  The reference tensors are dense f32 ([n,24,R,R] planes, [n,8R+8,R,R] mask) holding
+// ~40 and ~19 ones per game among 4,704 and 23,520 cells; writing them is the HBM-bound part of the
+// path (113 KB per game at 14x14).  rules_kernel produces them as bit sets (1 bit per cell, 3.5 KB
+// per game); expand_kernel streams the bits out as f32.  The two kernels run on different streams so
+// that the expansion of one batch overlaps the integer work of the next (FPC_FLAG_ASYNC_DENSE,
+// fpc_join).
+
+#define CK(expr)                                   \
+  do {                                             \
+    int rc_ = cuda_check((expr), #expr);           \
+    if (rc_ != FPC_OK) return rc_;                 \
+  } while (0)
 
 template <class G>
 __device__ __forceinline__ void load_record(WarpScratch<G> &s, const uint8_t *rec_g, int lane) {
@@ -82,26 +96,11 @@ __device__ __forceinline__ void store_record(WarpScratch<G> &s, uint8_t *rec_g, 
   if (lane < G::REC / 16) reinterpret_cast<uint4 *>(rec_g)[lane] = reinterpret_cast<const uint4 *>(s.rec)[lane];
 }
 
-// Stream one bit-plane set out as dense f32 (0.0 / 1.0): every warp store instruction
-// covers 512 contiguous bytes.
-template <int NFLOATS>
-__device__ __forceinline__ void stream_bits_as_f32(const uint32_t *bits, float *dst, int lane) {
-  constexpr int NF4 = NFLOATS / 4;
-  float4 *out = reinterpret_cast<float4 *>(dst);
-#pragma unroll 4
-  for (int f4 = lane; f4 < NF4; f4 += 32) {
-    const uint32_t nib = (bits[f4 >> 3] >> ((f4 & 7) * 4)) & 15u;
-    float4 v;
-    v.x = (nib & 1u) ? 1.0f : 0.0f;
-    v.y = (nib & 2u) ? 1.0f : 0.0f;
-    v.z = (nib & 4u) ? 1.0f : 0.0f;
-    v.w = (nib & 8u) ? 1.0f : 0.0f;
-    __stcs(out + f4, v);
-  }
-}
-
+// The rules kernel: one warp per game.  Legal moves, result, the bit sets of the dense outputs,
+// and (playout) the move choice and make-move.  It touches only the board store and compact
+// per-game outputs.
 template <class G>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) observe_kernel(const __grid_constant__ ObserveParams P) {
+__global__ void __launch_bounds__(BLOCK_THREADS) rules_kernel(const __grid_constant__ ObserveParams P) {
   __shared__ WarpScratch<G> scratch[WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * WARPS_PER_BLOCK + wib;
@@ -109,16 +108,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) observe_kernel(const __g
   WarpScratch<G> &s = scratch[wib];
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  if (P.mask)
+  if (P.mask_bits)
     for (int i = lane; i < G::MASK_WORDS; i += 32) s.mask_bits[i] = 0;
-  if (P.planes)
+  if (P.plane_bits)
     for (int i = lane; i < G::PLANE_WORDS; i += 32) s.plane_bits[i] = 0;
   load_record<G>(s, P.boards_in + (size_t)g * G::REC, lane);
   const int turn = s.turn;
 
   // ---- piece scan: mover's piece list + input-plane bits (src/cpp/board.cpp:318-344) -----
   int rot = 0;
-  if (P.planes) {
+  if (P.plane_bits) {
     rot = P.k ? P.k[g] : (P.k_all < 0 ? turn : P.k_all);
     rot &= 3;
   }
@@ -139,7 +138,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) observe_kernel(const __g
       if (idx < 64) s.plist[idx] = (uint8_t)G::mb(r, c);
     }
     np += __popc(b);
-    if (P.planes && present(p)) {
+    if (P.plane_bits && present(p)) {
       // ch = ((color - turn) mod 4)*6 + type - 1, -1 wrapping to 23 (src/cpp/board.cpp:336)
       int ch = ((color_of(p) - turn) & 3) * 6 + type_of(p) - 1;
       if (ch < 0) ch += 24;
@@ -252,13 +251,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) observe_kernel(const __g
     if (P.playout && result == 0)
       pick = (uint32_t)(((mix64(P.seed, P.game[g], (uint64_t)P.ply[g]) >> 32) * (uint64_t)n_legal) >> 32);
     const bool want_lists = P.moves || P.flat;
-    if (want_lists || P.mask || P.playout) {
+    if (want_lists || P.mask_bits || P.playout) {
       for (int base = 0; base < n_legal; base += 32) {
         const int i = base + lane;
         if (i < n_legal) {
           const uint32_t mv = s.moves[i];
           const uint32_t flat = mv >> 17;
-          if (P.mask) atomicOr(&s.mask_bits[flat >> 5], 1u << (flat & 31));
+          if (P.mask_bits) atomicOr(&s.mask_bits[flat >> 5], 1u << (flat & 31));
           if (want_lists || P.playout) {
             int rank = 0;
             for (int j = 0; j < n_legal; ++j) rank += s.moves[j] < mv;
@@ -275,9 +274,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) observe_kernel(const __g
     }
   }
 
-  // ---- dense outputs ---------------------------------------------------------------------
-  if (P.planes) stream_bits_as_f32<G::SSZ>(s.plane_bits, P.planes + (size_t)g * G::SSZ, lane);
-  if (P.mask) stream_bits_as_f32<G::ASZ>(s.mask_bits, P.mask + (size_t)g * G::ASZ, lane);
+  // ---- bit sets of the dense outputs (coalesced; expand_kernel turns them into f32) --------------
+  __syncwarp();
+  if (P.plane_bits)
+    for (int i = lane; i < G::PLANE_WORDS; i += 32) P.plane_bits[(size_t)g * G::PLANE_WORDS + i] = s.plane_bits[i];
+  if (P.mask_bits)
+    for (int i = lane; i < G::MASK_WORDS; i += 32) P.mask_bits[(size_t)g * G::MASK_WORDS + i] = s.mask_bits[i];
 
   // ---- playout: play the chosen move or re-seed the slot ------------------------------------
   if (P.playout) {
@@ -324,6 +326,55 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) observe_kernel(const __g
     }
   }
   if (lane == 0 && P.status) P.status[g] = status;
+}
+
+// bits -> dense f32 (0.0 / 1.0).  One tensor per launch half: games x (words_per_game words ->
+// floats_per_game floats).  A warp takes 32 words of one game per iteration with one coalesced
+// load, hands them round with shuffles and issues 8 store instructions of 512 contiguous bytes.
+// Pure streaming: no shared memory, one pass, HBM-write bound.
+constexpr int EXPAND_THREADS = 256;
+constexpr int EXPAND_ITERS = 2;  // 32-word groups per warp
+
+struct ExpandHalf {
+  const uint32_t *bits;  // [n][words]
+  float *out;            // [n][floats]
+  int words, floats, groups;  // per game; groups = ceil(words / 32)
+};
+
+__global__ void __launch_bounds__(EXPAND_THREADS)
+    expand_kernel(const __grid_constant__ ExpandHalf A, const __grid_constant__ ExpandHalf B, int n) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long warp = (unsigned long long)blockIdx.x * (EXPAND_THREADS / 32) + (threadIdx.x >> 5);
+  const unsigned long long total_a = (unsigned long long)n * A.groups, total_b = (unsigned long long)n * B.groups;
+#pragma unroll 1
+  for (int it = 0; it < EXPAND_ITERS; ++it) {
+    unsigned long long grp = warp * EXPAND_ITERS + it;
+    const ExpandHalf *H = &A;
+    if (grp >= total_a) {
+      grp -= total_a;
+      if (grp >= total_b) return;
+      H = &B;
+    }
+    const unsigned long long game = grp / H->groups;
+    const int w0 = (int)(grp - game * H->groups) * 32;
+    const uint32_t mine = w0 + lane < H->words ? __ldg(H->bits + game * H->words + w0 + lane) : 0u;
+    float4 *dst = reinterpret_cast<float4 *>(H->out + game * H->floats);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // store j, lane l: float4 number w0*8 + j*32 + l of this game = word w0 + j*4 + l/8, nibble l%8
+      const uint32_t w = __shfl_sync(FULL, mine, j * 4 + (lane >> 3));
+      const uint32_t nib = (w >> ((lane & 7) * 4)) & 15u;
+      const int f4 = w0 * 8 + j * 32 + lane;
+      if (f4 * 4 < H->floats) {
+        float4 v;
+        v.x = (nib & 1u) ? 1.0f : 0.0f;
+        v.y = (nib & 2u) ? 1.0f : 0.0f;
+        v.z = (nib & 4u) ? 1.0f : 0.0f;
+        v.w = (nib & 8u) ? 1.0f : 0.0f;
+        __stcs(dst + f4, v);
+      }
+    }
+  }
 }
 
 // chess::Board::MakeMove (engine/board.cpp:1028-1096) for arbitrary 8-byte moves, or for
@@ -444,12 +495,114 @@ static int cuda_check(cudaError_t e, const char *what) {
   return fail(FPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-template <class G>
-static int launch_observe(const ObserveParams &p, cudaStream_t st) {
+// Per host thread and device: the stream expand_kernel runs on, its events, and the double-buffered
+// bit-set workspace between rules_kernel and expand_kernel.
+struct SideState {
+  cudaStream_t side = nullptr;  // expand_kernel: lowest priority
+  cudaStream_t hi = nullptr;    // rules_kernel when dense outputs are wanted: highest priority, so that its
+                                // CTAs are dispatched ahead of the remaining CTAs of a running expansion
+  cudaEvent_t fork = nullptr;
+  cudaEvent_t rules_done[2] = {nullptr, nullptr}, expand_done[2] = {nullptr, nullptr};
+  bool expand_recorded[2] = {false, false};
+  uint32_t *bits[2] = {nullptr, nullptr};
+  size_t bits_words = 0;
+  int parity = 0;
+  int last = -1;  // buffer of the most recent expansion (fpc_join)
+};
+static thread_local SideState g_side[16];
+
+static int side_state(SideState **out, size_t words, cudaStream_t st) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return fail(FPC_ERR_ARG, "device ordinal out of range");
+  SideState &S = g_side[dev];
+  if (!S.side) {
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CK(cudaStreamCreateWithPriority(&S.side, cudaStreamNonBlocking, least));
+    CK(cudaStreamCreateWithPriority(&S.hi, cudaStreamNonBlocking, greatest));
+    CK(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&S.rules_done[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&S.expand_done[i], cudaEventDisableTiming));
+    }
+  }
+  if (words > S.bits_words) {
+    // growing the workspace: earlier launches may still use the old one
+    if (S.bits[0]) {
+      CK(cudaStreamSynchronize(st));
+      CK(cudaStreamSynchronize(S.side));
+      cudaFree(S.bits[0]);
+      cudaFree(S.bits[1]);
+      S.bits[0] = S.bits[1] = nullptr;
+      S.bits_words = 0;
+    }
+    CK(cudaMalloc(&S.bits[0], words * sizeof(uint32_t)));
+    CK(cudaMalloc(&S.bits[1], words * sizeof(uint32_t)));
+    S.bits_words = words;
+  }
+  *out = &S;
+  return FPC_OK;
+}
+
+struct DenseOut {
+  float *planes, *mask;
+  int flags;
+};
+
+// rules_kernel on the caller's stream; expand_kernel on the side stream once the rules kernel has
+// written the bit sets.  Unless FPC_FLAG_ASYNC_DENSE is set the caller's stream then waits for the
+// expansion.  after_rules (may be a no-op) runs right after the rules kernel is enqueued: the
+// host-buffer entry points start their device-to-host copies of the compact results there.
+template <class G, class F>
+static int launch_observe(ObserveParams p, DenseOut d, cudaStream_t st, F after_rules) {
   if (p.n == 0) return FPC_OK;
+  const bool dense = d.planes || d.mask;
+  SideState *S = nullptr;
+  int b = 0;
+  if (dense) {
+    if ((reinterpret_cast<uintptr_t>(d.planes) | reinterpret_cast<uintptr_t>(d.mask)) & 15)
+      return fail(FPC_ERR_ARG, "planes / mask must be 16-byte aligned");
+    const size_t pw = (size_t)p.n * G::PLANE_WORDS, mw = (size_t)p.n * G::MASK_WORDS;
+    int rc = side_state(&S, pw + mw, st);
+    if (rc != FPC_OK) return rc;
+    b = S->parity;
+    S->parity ^= 1;
+    p.plane_bits = d.planes ? S->bits[b] : nullptr;
+    p.mask_bits = d.mask ? S->bits[b] + pw : nullptr;
+  }
   const int blocks = (p.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-  observe_kernel<G><<<blocks, WARPS_PER_BLOCK * 32, 0, st>>>(p);
-  return cuda_check(cudaGetLastError(), "observe_kernel launch");
+  if (!dense) {
+    rules_kernel<G><<<blocks, BLOCK_THREADS, 0, st>>>(p);
+    CK(cudaGetLastError());
+    return after_rules();
+  }
+  // fork: caller's stream -> high-priority stream (rules) -> back to the caller's stream; the
+  // expansion that last read this bit buffer must be done before the rules kernel rewrites it
+  CK(cudaEventRecord(S->fork, st));
+  CK(cudaStreamWaitEvent(S->hi, S->fork, 0));
+  if (S->expand_recorded[b]) CK(cudaStreamWaitEvent(S->hi, S->expand_done[b], 0));
+  rules_kernel<G><<<blocks, BLOCK_THREADS, 0, S->hi>>>(p);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(S->rules_done[b], S->hi));
+  CK(cudaStreamWaitEvent(st, S->rules_done[b], 0));
+  int rc = after_rules();
+  if (rc != FPC_OK) return rc;
+  {
+    CK(cudaStreamWaitEvent(S->side, S->rules_done[b], 0));
+    ExpandHalf A{p.plane_bits, d.planes, G::PLANE_WORDS, G::SSZ, d.planes ? (G::PLANE_WORDS + 31) / 32 : 0};
+    ExpandHalf B{p.mask_bits, d.mask, G::MASK_WORDS, G::ASZ, d.mask ? (G::MASK_WORDS + 31) / 32 : 0};
+    const unsigned long long groups = (unsigned long long)p.n * (A.groups + B.groups);
+    const unsigned long long warps = (groups + EXPAND_ITERS - 1) / EXPAND_ITERS;
+    const unsigned long long grid = (warps + EXPAND_THREADS / 32 - 1) / (EXPAND_THREADS / 32);
+    expand_kernel<<<(unsigned)grid, EXPAND_THREADS, 0, S->side>>>(A, B, p.n);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(S->expand_done[b], S->side));
+    S->expand_recorded[b] = true;
+    S->last = b;
+    if (!(d.flags & FPC_FLAG_ASYNC_DENSE)) CK(cudaStreamWaitEvent(st, S->expand_done[b], 0));
+  }
+  return FPC_OK;
 }
 template <class G>
 static int launch_make(const uint8_t *in, const uint64_t *moves, const int32_t *flat, int n, uint8_t *out,
@@ -478,7 +631,13 @@ static int launch_heuristic(const uint8_t *in, int n, int32_t *v, cudaStream_t s
 
 static int ia_of(int R) { return R == 14 || R == 13 ? 3 : (R == 10 || R == 8 ? 2 : -1); }
 
-static int do_observe(int R, const ObserveParams &p, cudaStream_t st) { FPC_DISPATCH(R, launch_observe<G>(p, st)); }
+template <class F>
+static int do_observe(int R, const ObserveParams &p, DenseOut d, cudaStream_t st, F after_rules) {
+  FPC_DISPATCH(R, (launch_observe<G>(p, d, st, after_rules)));
+}
+static int do_observe(int R, const ObserveParams &p, DenseOut d, cudaStream_t st) {
+  return do_observe(R, p, d, st, [] { return FPC_OK; });
+}
 static int do_make(int R, const uint8_t *in, const uint64_t *moves, const int32_t *flat, int n, uint8_t *out,
                    int32_t *err, cudaStream_t st) {
   FPC_DISPATCH(R, launch_make<G>(in, moves, flat, n, out, err, st));
@@ -543,8 +702,18 @@ int fpc_move_flat_index(int R, uint64_t move) {
   return plane * R * R + (from / R) * R + from % R;
 }
 
+int fpc_join(void *stream) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return fail(FPC_ERR_ARG, "device ordinal out of range");
+  SideState &S = g_side[dev];
+  if (S.last >= 0) CK(cudaStreamWaitEvent((cudaStream_t)stream, S.expand_done[S.last], 0));
+  return FPC_OK;
+}
+
 int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_t *d_flat, int32_t *d_counts,
-                int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all, float *d_mask, void *stream) {
+                int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all, float *d_mask, int flags,
+                void *stream) {
   if (n < 0 || (n > 0 && !d_boards)) return fail(FPC_ERR_ARG, "fpc_observe: bad boards/n");
   ObserveParams p{};
   p.boards_in = d_boards;
@@ -554,16 +723,16 @@ int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_
   p.flat = d_flat;
   p.counts = d_counts;
   p.status = d_status;
-  p.planes = d_planes;
   p.k = d_k;
   p.k_all = k_all;
-  p.mask = d_mask;
-  return do_observe(R, p, (cudaStream_t)stream);
+  return do_observe(R, p, DenseOut{d_planes, d_mask, flags}, (cudaStream_t)stream);
 }
 
-int fpc_encode(int R, const uint8_t *d_boards, int n, const int32_t *d_k, int k_all, float *d_planes, void *stream) {
+int fpc_encode(int R, const uint8_t *d_boards, int n, const int32_t *d_k, int k_all, float *d_planes, int flags,
+               void *stream) {
   if (!d_planes && n > 0) return fail(FPC_ERR_ARG, "fpc_encode: null output");
-  return fpc_observe(R, d_boards, n, nullptr, nullptr, nullptr, nullptr, d_planes, d_k, k_all, nullptr, stream);
+  return fpc_observe(R, d_boards, n, nullptr, nullptr, nullptr, nullptr, d_planes, d_k, k_all, nullptr, flags,
+                     stream);
 }
 
 int fpc_make_moves(int R, const uint8_t *d_in, const uint64_t *d_moves, int n, uint8_t *d_out, int32_t *d_err,
@@ -583,23 +752,21 @@ int fpc_heuristic(int R, const uint8_t *d_boards, int n, int32_t *d_value, void 
   return do_heuristic(R, d_boards, n, d_value, (cudaStream_t)stream);
 }
 
-int fpc_playout_step(int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d_game, int32_t *d_ply,
-                     const uint8_t *d_start, int max_plies, uint64_t game_stride, uint64_t *d_chosen,
-                     int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all,
-                     float *d_mask, uint64_t *d_counters, void *stream) {
+static int playout_params(ObserveParams &p, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d_game, int32_t *d_ply,
+                          const uint8_t *d_start, int max_plies, uint64_t game_stride, uint64_t *d_chosen,
+                          int32_t *d_counts, int32_t *d_status, const int32_t *d_k, int k_all,
+                          uint64_t *d_counters) {
   if (n < 0 || (n > 0 && (!d_boards || !d_game || !d_ply || !d_start)) || max_plies <= 0)
     return fail(FPC_ERR_ARG, "fpc_playout_step: bad argument");
-  ObserveParams p{};
+  p = ObserveParams{};
   p.boards_in = d_boards;
   p.boards_out = d_boards;
   p.n = n;
   p.need_movegen = 1;
   p.counts = d_counts;
   p.status = d_status;
-  p.planes = d_planes;
   p.k = d_k;
   p.k_all = k_all;
-  p.mask = d_mask;
   p.playout = 1;
   p.seed = seed;
   p.game = d_game;
@@ -609,7 +776,18 @@ int fpc_playout_step(int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d
   p.game_stride = game_stride;
   p.chosen = d_chosen;
   p.counters = reinterpret_cast<unsigned long long *>(d_counters);
-  return do_observe(R, p, (cudaStream_t)stream);
+  return FPC_OK;
+}
+
+int fpc_playout_step(int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d_game, int32_t *d_ply,
+                     const uint8_t *d_start, int max_plies, uint64_t game_stride, uint64_t *d_chosen,
+                     int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all,
+                     float *d_mask, uint64_t *d_counters, int flags, void *stream) {
+  ObserveParams p;
+  int rc = playout_params(p, d_boards, n, seed, d_game, d_ply, d_start, max_plies, game_stride, d_chosen, d_counts,
+                          d_status, d_k, k_all, d_counters);
+  if (rc != FPC_OK) return rc;
+  return do_observe(R, p, DenseOut{d_planes, d_mask, flags}, (cudaStream_t)stream);
 }
 
 // ---- host-buffer context ---------------------------------------------------------------------
@@ -622,12 +800,6 @@ struct fpc_ctx {
   int32_t *d_flat, *d_counts, *d_status, *d_ply, *d_err;
   float *d_planes, *d_mask;   // lazily allocated for host-destination dense outputs
 };
-
-#define CK(expr)                                   \
-  do {                                             \
-    int rc_ = cuda_check((expr), #expr);           \
-    if (rc_ != FPC_OK) return rc_;                 \
-  } while (0)
 
 fpc_ctx *fpc_ctx_create(int device, int R, int max_n) {
   if (!fpc_supported(R) || max_n <= 0) {
@@ -713,7 +885,7 @@ int fpc_host_observe(fpc_ctx *c, const uint8_t *h_boards, int n, uint64_t *h_mov
   CK(cudaMemcpyAsync(c->d_boards, h_boards, N * c->rec, cudaMemcpyHostToDevice, c->stream));
   rc = fpc_observe(c->R, c->d_boards, n, h_moves ? c->d_moves : nullptr, h_flat ? c->d_flat : nullptr,
                    (h_counts || h_moves || h_flat) ? c->d_counts : nullptr, h_status ? c->d_status : nullptr,
-                   d_planes, nullptr, k_all, d_mask, c->stream);
+                   d_planes, nullptr, k_all, d_mask, 0, c->stream);
   if (rc != FPC_OK) return rc;
   if (h_counts) CK(cudaMemcpyAsync(h_counts, c->d_counts, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   if (h_status) CK(cudaMemcpyAsync(h_status, c->d_status, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -770,14 +942,20 @@ int fpc_host_playout_step(fpc_ctx *c, uint8_t *h_boards, int n, uint64_t seed, u
   CK(cudaMemcpyAsync(c->d_game, h_game, N * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_ply, h_ply, N * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_start, h_start, c->rec, cudaMemcpyHostToDevice, c->stream));
-  rc = fpc_playout_step(c->R, c->d_boards, n, seed, c->d_game, c->d_ply, c->d_start, max_plies, game_stride, nullptr,
-                        c->d_counts, c->d_status, d_planes, nullptr, k_all, d_mask, nullptr, c->stream);
+  ObserveParams p;
+  rc = playout_params(p, c->d_boards, n, seed, c->d_game, c->d_ply, c->d_start, max_plies, game_stride, nullptr,
+                      c->d_counts, c->d_status, nullptr, k_all, nullptr);
   if (rc != FPC_OK) return rc;
-  CK(cudaMemcpyAsync(h_boards, c->d_boards, N * c->rec, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(h_game, c->d_game, N * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(h_ply, c->d_ply, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  if (h_counts) CK(cudaMemcpyAsync(h_counts, c->d_counts, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  if (h_status) CK(cudaMemcpyAsync(h_status, c->d_status, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  // the compact results go back to the host while the dense outputs are still being written
+  rc = do_observe(c->R, p, DenseOut{d_planes, d_mask, 0}, c->stream, [&]() -> int {
+    CK(cudaMemcpyAsync(h_boards, c->d_boards, N * c->rec, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_game, c->d_game, N * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_ply, c->d_ply, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (h_counts) CK(cudaMemcpyAsync(h_counts, c->d_counts, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (h_status) CK(cudaMemcpyAsync(h_status, c->d_status, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    return FPC_OK;
+  });
+  if (rc != FPC_OK) return rc;
   CK(cudaStreamSynchronize(c->stream));
   return FPC_OK;
 }

@@ -86,11 +86,22 @@ int fpc_move_flat_index(int R, uint64_t move);      /* Move::GetFlatIndex, -1 wh
  *   flat indices     = Board::GetLegalMovesIndices (src/cpp/board.cpp:424-449) as flat indices
  * Any output pointer may be NULL.  d_moves / d_flat are [n][FPC_MAX_MOVES]. */
 int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_t *d_flat, int32_t *d_counts,
-                int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all, float *d_mask, void *stream);
+                int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all, float *d_mask, int flags,
+                void *stream);
+
+/* Dense outputs and streams.  The compact results (moves, counts, status, boards) are written by
+ * rules_kernel on `stream`.  The dense f32 planes / mask are written by expand_kernel on an
+ * internal second stream as soon as the rules kernel has produced their bit sets; by default
+ * `stream` then waits for it, so everything is ordered on `stream` as usual.  With
+ * FPC_FLAG_ASYNC_DENSE that wait is left out: the next call's rules kernel overlaps this call's
+ * expansion (the HBM-bound part), and the caller orders a consumer of the dense tensors with
+ * fpc_join(consumer_stream).  State is per host thread and device. */
+#define FPC_FLAG_ASYNC_DENSE 1
+int fpc_join(void *stream);
 
 /* Board::GetEncodedStates alone (no move generation). */
 int fpc_encode(int R, const uint8_t *d_boards, int n, const int32_t *d_k, int k_all, float *d_planes,
-               void *stream);
+               int flags, void *stream);
 
 /* chess::Board::MakeMove (engine/board.cpp:1028-1096) with full generator moves, as used by
  * Board::TakeAction (src/cpp/board.cpp:234-239).  d_err[g] = FPC_OK or FPC_ERR_MOVE.
@@ -118,7 +129,7 @@ int fpc_heuristic(int R, const uint8_t *d_boards, int n, int32_t *d_value, void 
 int fpc_playout_step(int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d_game, int32_t *d_ply,
                      const uint8_t *d_start, int max_plies, uint64_t game_stride, uint64_t *d_chosen,
                      int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all,
-                     float *d_mask, uint64_t *d_counters, void *stream);
+                     float *d_mask, uint64_t *d_counters, int flags, void *stream);
 
 /* ---- host-buffer operations (per-object calls of the binding; e2e measurement) ------------- */
 

@@ -34,7 +34,7 @@ def gpu_perft(name, depth, castling):
         counts = torch.zeros(n, dtype=torch.int32, device="cuda")
         moves = torch.zeros((n, _lib.FPC_MAX_MOVES), dtype=torch.int64, device="cuda")
         _lib.check(L.fpc_observe(R, frontier.data_ptr(), n, moves.data_ptr(), None, counts.data_ptr(), None,
-                                 None, None, -1, None, None))
+                                 None, None, -1, None, 0, None))
         out.append(int(counts.sum().item()))
         if d == depth - 1:
             break
@@ -239,9 +239,9 @@ def test_edge_cases_empty_ragged_terminal():
     L = _lib.lib()
     o = oracle_for(R)
     # n = 0 is a no-op
-    _lib.check(L.fpc_observe(R, None, 0, None, None, None, None, None, None, -1, None, None))
+    _lib.check(L.fpc_observe(R, None, 0, None, None, None, None, None, None, -1, None, 0, None))
     # unsupported geometry
-    assert L.fpc_observe(12, None, 0, None, None, None, None, None, None, -1, None, None) == _lib.FPC_ERR_ARG
+    assert L.fpc_observe(12, None, 0, None, None, None, None, None, None, -1, None, 0, None) == _lib.FPC_ERR_ARG
     recs = []
     # (a) mover has no king -> other team wins, no moves (engine/board.cpp:852-856, 895-899)
     r = start_record("STANDARD")
@@ -283,6 +283,29 @@ def test_edge_cases_empty_ragged_terminal():
         assert (status[i] & 3) == res, i
     assert np.array_equal(env.mask_buffer().cpu().numpy(), o.mask(recs))
     assert np.array_equal(env.planes_buffer().cpu().numpy(), o.encode(recs, recs[:, g.off_turn].astype(np.int32)))
+
+
+def test_async_dense_pipeline_matches_sync():
+    """FPC_FLAG_ASYNC_DENSE: the expansion of step t overlaps the rules of step t+1; after fpc_join the
+    dense tensors are those of the last step, bit-identical to the synchronous path and the oracle."""
+    R, n = 14, 1024
+    g = GEOMETRIES[R]
+    o = oracle_for(R)
+    start = start_record("STANDARD", castling=True)
+    a, b = BatchedEnv(R, n), BatchedEnv(R, n)
+    a.reset_playout(start)
+    b.reset_playout(start)
+    for step in range(40):
+        before = a.boards.clone()
+        a.playout_step(seed=SEED, planes=True, mask=True, async_dense=True)
+        b.playout_step(seed=SEED, planes=True, mask=True)
+    a.join()
+    torch.cuda.synchronize()
+    assert torch.equal(a.boards, b.boards)
+    assert torch.equal(a.planes_buffer(), b.planes_buffer()) and torch.equal(a.mask_buffer(), b.mask_buffer())
+    recs = before[:256].cpu().numpy()
+    assert np.array_equal(a.planes_buffer()[:256].cpu().numpy(), o.encode(recs, recs[:, g.off_turn].astype(np.int32)))
+    assert np.array_equal(a.mask_buffer()[:256].cpu().numpy(), o.mask(recs))
 
 
 def test_full_size_properties():
