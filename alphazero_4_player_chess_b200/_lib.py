@@ -44,7 +44,8 @@ SIGNATURES = {
     "fpc_host_observe": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "fpc_host_make_moves": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "fpc_host_make_index": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
-    "fpc_host_playout_step": (_i, [_vp, _vp, _i, _u64, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _i, _vp]),
+    "fpc_host_playout_step": (_i, [_vp, _vp, _i, _u64, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _i, _vp, _i]),
+    "fpc_ctx_sync": (_i, [_vp]),
 }
 
 _LIB = None

@@ -112,6 +112,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) rules_kernel(const __grid_const
     for (int i = lane; i < G::MASK_WORDS; i += 32) s.mask_bits[i] = 0;
   if (P.plane_bits)
     for (int i = lane; i < G::PLANE_WORDS; i += 32) s.plane_bits[i] = 0;
+  // playout bookkeeping is read up front: with zero-copy host buffers each load is a PCIe round trip
+  const uint64_t game_id = P.playout ? P.game[g] : 0;
+  const int ply = P.playout ? P.ply[g] : 0;
   load_record<G>(s, P.boards_in + (size_t)g * G::REC, lane);
   const int turn = s.turn;
 
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) rules_kernel(const __grid_const
     // ---- canonical order: rank = number of smaller keys (keys are unique) ------------------
     uint32_t pick = 0xffffffffu;
     if (P.playout && result == 0)
-      pick = (uint32_t)(((mix64(P.seed, P.game[g], (uint64_t)P.ply[g]) >> 32) * (uint64_t)n_legal) >> 32);
+      pick = (uint32_t)(((mix64(P.seed, game_id, (uint64_t)ply) >> 32) * (uint64_t)n_legal) >> 32);
     const bool want_lists = P.moves || P.flat;
     if (want_lists || P.mask_bits || P.playout) {
       for (int base = 0; base < n_legal; base += 32) {
@@ -285,7 +288,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS) rules_kernel(const __grid_const
   if (P.playout) {
     const unsigned who = __ballot_sync(FULL, chosen_mv != 0);
     const int result = status & FPC_STATUS_RESULT_MASK;
-    const int ply = P.ply[g];
     uint64_t chosen64 = 0;
     bool finished = false;
     if (result == 0 && who) {
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) rules_kernel(const __grid_const
     if (lane == 0) {
       if (P.chosen) P.chosen[g] = chosen64;
       if (finished) {
-        P.game[g] += P.game_stride;
+        P.game[g] = game_id + P.game_stride;
         P.ply[g] = 0;
       } else {
         P.ply[g] = ply + 1;
@@ -799,6 +801,8 @@ struct fpc_ctx {
   uint64_t *d_moves, *d_game;
   int32_t *d_flat, *d_counts, *d_status, *d_ply, *d_err;
   float *d_planes, *d_mask;   // lazily allocated for host-destination dense outputs
+  uint8_t h_start_cache[256];
+  bool start_valid;
 };
 
 fpc_ctx *fpc_ctx_create(int device, int R, int max_n) {
@@ -859,10 +863,19 @@ void fpc_ctx_destroy(fpc_ctx *c) {
 
 void *fpc_ctx_stream(fpc_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
+
 static int ctx_check(fpc_ctx *c, int n, const char *who) {
   if (!c) return fail(FPC_ERR_ARG, std::string(who) + ": null context");
   if (n < 0 || n > c->max_n) return fail(FPC_ERR_ARG, std::string(who) + ": n exceeds the context capacity");
   return cuda_check(cudaSetDevice(c->device), "cudaSetDevice");
+}
+
+int fpc_ctx_sync(fpc_ctx *c) {
+  int rc = ctx_check(c, 0, "fpc_ctx_sync");
+  if (rc != FPC_OK) return rc;
+  rc = fpc_join(c->stream);
+  if (rc != FPC_OK) return rc;
+  return cuda_check(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
 }
 
 int fpc_host_observe(fpc_ctx *c, const uint8_t *h_boards, int n, uint64_t *h_moves, int32_t *h_flat,
@@ -930,24 +943,55 @@ int fpc_host_make_index(fpc_ctx *c, const uint8_t *h_in, const int32_t *h_flat, 
   return host_make(c, h_in, nullptr, h_flat, n, h_out, h_err);
 }
 
+// Device alias of a pinned (page-locked, mapped) host pointer, or null for pageable memory.
+static void *mapped_alias(const void *h) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, h) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 int fpc_host_playout_step(fpc_ctx *c, uint8_t *h_boards, int n, uint64_t seed, uint64_t *h_game, int32_t *h_ply,
                           const uint8_t *h_start, int max_plies, uint64_t game_stride, int32_t *h_counts,
-                          int32_t *h_status, float *d_planes, int k_all, float *d_mask) {
+                          int32_t *h_status, float *d_planes, int k_all, float *d_mask, int flags) {
   int rc = ctx_check(c, n, "fpc_host_playout_step");
   if (rc != FPC_OK) return rc;
   if (n == 0) return FPC_OK;
   if (!h_boards || !h_game || !h_ply || !h_start) return fail(FPC_ERR_ARG, "fpc_host_playout_step: null argument");
   const size_t N = (size_t)n;
+  // the start record only changes between runs: upload it when it differs from the cached copy
+  if (!c->start_valid || memcmp(c->h_start_cache, h_start, c->rec) != 0) {
+    memcpy(c->h_start_cache, h_start, c->rec);
+    CK(cudaMemcpyAsync(c->d_start, c->h_start_cache, c->rec, cudaMemcpyHostToDevice, c->stream));
+    c->start_valid = true;
+  }
+  ObserveParams p;
+  // Zero-copy: when every host buffer is pinned, the rules kernel reads the records straight from
+  // host memory and writes its results straight back over PCIe -- no staging copies, one launch.
+  uint8_t *m_boards = (uint8_t *)mapped_alias(h_boards);
+  uint64_t *m_game = (uint64_t *)mapped_alias(h_game);
+  int32_t *m_ply = (int32_t *)mapped_alias(h_ply);
+  int32_t *m_counts = h_counts ? (int32_t *)mapped_alias(h_counts) : nullptr;
+  int32_t *m_status = h_status ? (int32_t *)mapped_alias(h_status) : nullptr;
+  if (m_boards && m_game && m_ply && (!h_counts || m_counts) && (!h_status || m_status)) {
+    rc = playout_params(p, m_boards, n, seed, m_game, m_ply, c->d_start, max_plies, game_stride, nullptr, m_counts,
+                        m_status, nullptr, k_all, nullptr);
+    if (rc != FPC_OK) return rc;
+    rc = do_observe(c->R, p, DenseOut{d_planes, d_mask, flags}, c->stream);
+    if (rc != FPC_OK) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return FPC_OK;
+  }
   CK(cudaMemcpyAsync(c->d_boards, h_boards, N * c->rec, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_game, h_game, N * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_ply, h_ply, N * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_start, h_start, c->rec, cudaMemcpyHostToDevice, c->stream));
-  ObserveParams p;
   rc = playout_params(p, c->d_boards, n, seed, c->d_game, c->d_ply, c->d_start, max_plies, game_stride, nullptr,
                       c->d_counts, c->d_status, nullptr, k_all, nullptr);
   if (rc != FPC_OK) return rc;
   // the compact results go back to the host while the dense outputs are still being written
-  rc = do_observe(c->R, p, DenseOut{d_planes, d_mask, 0}, c->stream, [&]() -> int {
+  rc = do_observe(c->R, p, DenseOut{d_planes, d_mask, flags}, c->stream, [&]() -> int {
     CK(cudaMemcpyAsync(h_boards, c->d_boards, N * c->rec, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(h_game, c->d_game, N * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(h_ply, c->d_ply, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

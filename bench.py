@@ -279,17 +279,19 @@ def run_ours(args) -> None:
         _lib.check(L.fpc_host_playout_step(ctx, h_boards.data_ptr(), N_GAMES, SEED, h_game.data_ptr(),
                                            h_ply.data_ptr(), h_start.data_ptr(), MAX_PLIES, stride,
                                            h_counts.data_ptr(), h_status.data_ptr(), d_planes.data_ptr(), -1,
-                                           d_mask.data_ptr()))
+                                           d_mask.data_ptr(), _lib.FLAG_ASYNC_DENSE))
 
     e2e_steps = args.steps
     for _ in range(max(args.warmup, 3)):
         e2e_step()
+    _lib.check(L.fpc_ctx_sync(ctx))
     barrier()
     t0 = time.perf_counter()
     legal_seen = 0
     for _ in range(e2e_steps):
-        e2e_step()  # synchronous: returns after the D2H copies have landed
+        e2e_step()  # returns after the D2H copies of this step's results have landed
         legal_seen += int(h_counts[0])
+    _lib.check(L.fpc_ctx_sync(ctx))  # ... and the last step's dense tensors are complete
     dt = time.perf_counter() - t0
     barrier()
     L.fpc_ctx_destroy(ctx)
@@ -320,7 +322,8 @@ def run_ours(args) -> None:
             "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "fpc_host_playout_step: boards/game ids/plies from pinned host memory and back every "
-                            "step; planes+mask left on the device as the reference's device='cuda' does"},
+                            "step (the call returns when they have landed); planes+mask are left on the device "
+                            "as the reference's device='cuda' does, their expansion overlapping the next step"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

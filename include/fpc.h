@@ -152,10 +152,14 @@ int fpc_host_make_moves(fpc_ctx *ctx, const uint8_t *h_in, const uint64_t *h_mov
 int fpc_host_make_index(fpc_ctx *ctx, const uint8_t *h_in, const int32_t *h_flat, int n, uint8_t *h_out,
                         int32_t *h_err);
 /* One playout ply through host buffers: boards, game ids and plies are copied in, stepped and
- * copied back; planes/mask stay on the device (d_planes/d_mask may be NULL). */
+ * copied back; planes/mask stay on the device (d_planes/d_mask may be NULL).  The call returns when
+ * the host buffers hold the results.  With FPC_FLAG_ASYNC_DENSE it does not wait for the dense
+ * tensors: their expansion overlaps the next call, and fpc_ctx_sync() waits for it. */
 int fpc_host_playout_step(fpc_ctx *ctx, uint8_t *h_boards, int n, uint64_t seed, uint64_t *h_game,
                           int32_t *h_ply, const uint8_t *h_start, int max_plies, uint64_t game_stride,
-                          int32_t *h_counts, int32_t *h_status, float *d_planes, int k_all, float *d_mask);
+                          int32_t *h_counts, int32_t *h_status, float *d_planes, int k_all, float *d_mask,
+                          int flags);
+int fpc_ctx_sync(fpc_ctx *ctx);
 
 #ifdef __cplusplus
 }

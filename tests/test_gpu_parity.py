@@ -233,6 +233,46 @@ def test_host_api_matches_device_api():
         L.fpc_ctx_destroy(ctx)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_playout_step_zero_copy_and_staged(pinned):
+    """fpc_host_playout_step: pinned host buffers are read/written by the kernel directly (zero-copy),
+    pageable ones go through staging copies; both must replay the device-resident env exactly."""
+    R, n, steps = 14, 512, 60
+    L = _lib.lib()
+    g = GEOMETRIES[R]
+    start = start_record("STANDARD", castling=True)
+    env = BatchedEnv(R, n)
+    env.reset_playout(start)
+    mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    h_boards = mk(torch.from_numpy(np.broadcast_to(start, (n, g.record_bytes)).copy()))
+    h_game = mk(torch.arange(n, dtype=torch.int64))
+    h_ply = mk(torch.zeros(n, dtype=torch.int32))
+    h_counts = mk(torch.zeros(n, dtype=torch.int32))
+    h_status = mk(torch.zeros(n, dtype=torch.int32))
+    h_start = torch.from_numpy(start.copy())
+    planes = torch.empty((n, 24, R, R), dtype=torch.float32, device="cuda")
+    mask = torch.empty((n, g.num_action_channels, R, R), dtype=torch.float32, device="cuda")
+    ctx = L.fpc_ctx_create(0, R, n)
+    assert ctx, L.fpc_last_error()
+    try:
+        for step in range(steps):
+            flags = _lib.FLAG_ASYNC_DENSE if step % 2 else 0
+            _lib.check(L.fpc_host_playout_step(ctx, h_boards.data_ptr(), n, SEED, h_game.data_ptr(), h_ply.data_ptr(),
+                                               h_start.data_ptr(), 40, n, h_counts.data_ptr(), h_status.data_ptr(),
+                                               planes.data_ptr(), -1, mask.data_ptr(), flags))
+            env.playout_step(seed=SEED, max_plies=40, planes=True, mask=True)
+            torch.cuda.synchronize()
+            assert np.array_equal(h_boards.numpy(), env.boards.cpu().numpy()), step
+            assert np.array_equal(h_game.numpy(), env.game.cpu().numpy())
+            assert np.array_equal(h_ply.numpy(), env.ply.cpu().numpy())
+            assert np.array_equal(h_counts.numpy(), env.counts.cpu().numpy())
+            assert np.array_equal(h_status.numpy(), env.status.cpu().numpy())
+        _lib.check(L.fpc_ctx_sync(ctx))
+        assert torch.equal(planes, env.planes_buffer()) and torch.equal(mask, env.mask_buffer())
+    finally:
+        L.fpc_ctx_destroy(ctx)
+
+
 def test_edge_cases_empty_ragged_terminal():
     R = 14
     g = GEOMETRIES[R]
