@@ -38,6 +38,9 @@ SIGNATURES = {
     "fpc_heuristic": (_i, [_i, _vp, _i, _vp, _vp]),
     "fpc_playout_step": (_i, [_i, _vp, _i, _u64, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _vp, _vp, _i, _vp,
                               _vp, _i, _vp]),
+    "fpc_tree_reset": (_i, [_vp, _vp, _vp]),
+    "fpc_tree_select": (_i, [_vp, _i, _vp, _vp]),
+    "fpc_tree_expand_backup": (_i, [_vp, _vp, _vp, _vp]),
     "fpc_ctx_create": (_vp, [_i, _i, _i]),
     "fpc_ctx_destroy": (None, [_vp]),
     "fpc_ctx_stream": (_vp, [_vp]),
@@ -47,6 +50,18 @@ SIGNATURES = {
     "fpc_host_playout_step": (_i, [_vp, _vp, _i, _u64, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _i, _vp, _i]),
     "fpc_ctx_sync": (_i, [_vp]),
 }
+
+
+
+class TreeDesc(C.Structure):
+    """struct fpc_tree (include/fpc.h): the caller-owned device arrays of the batched PUCT trees."""
+    _fields_ = ([("R", C.c_int32), ("n_games", C.c_int32), ("node_cap", C.c_int32), ("board_cap", C.c_int32),
+                 ("C", C.c_double)] +
+                [(name, C.c_void_p) for name in
+                 ("parent", "first_child", "n_children", "visits", "move_flat", "board_idx", "value_sum", "prior",
+                  "n_nodes", "n_boards", "leaf", "dropped", "error", "boards", "leaf_boards", "leaf_flat",
+                  "leaf_counts", "leaf_status", "k")])
+
 
 _LIB = None
 

@@ -9,9 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfpc.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["fpc_kernels.cu"]
+SOURCES = ["fpc_kernels.cu", "fpc_puct.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--use_fast_math", "-cudart", "shared"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-cudart", "shared"]
 
 
 def _stale() -> bool:

@@ -386,6 +386,64 @@ __device__ __forceinline__ void make_compact(WarpScratch<G> &s, uint32_t mv) {
   s.turn = (turn + 1) & 3;
 }
 
+// fpchess::Move(int flat_index) (src/cpp/move.cpp:41-61): from = the square, to = from.Relative(...),
+// G::NSQ where that leaves the R x R box (BoardLocation's "missing", engine/board.h:194-199).
+template <class G>
+__device__ __forceinline__ void decode_flat_move(int f, int &from, int &to) {
+  constexpr int R = G::R, NSQ = G::NSQ;
+  if (f < 0 || f >= G::ASZ) {
+    from = to = NSQ;
+    return;
+  }
+  const int type = f / NSQ, pos = f - type * NSQ;
+  const int row = pos / R, col = pos - row * R;
+  int dr, dc;
+  if (type < 8 * (R - 1)) {
+    const int dir = type / (R - 1), dist = type - dir * (R - 1) + 1;
+    const int d = qdelta(dir);
+    const int ur = (d + 24) / 16 - 1, uc = d - ur * 16;
+    dr = ur * dist;
+    dc = uc * dist;
+  } else {
+    int k = type - 8 * (R - 1);
+    if (k > 7) k = 7;
+    dr = kdrow(k);
+    dc = kdcol(k);
+  }
+  const int tr = row + dr, tc = col + dc;
+  from = pos;
+  to = ((unsigned)tr < (unsigned)R && (unsigned)tc < (unsigned)R) ? tr * R + tc : NSQ;
+}
+
+// chess::Board::MakeMove (engine/board.cpp:1028-1096) on the record bytes, for any 8-byte move image
+// (index-built moves carry promo = NO_PIECE, rook squares = NSQ, rights-after = 0).  Returns false for
+// "piece missing for move" (:1046-1054, thrown after the capture was removed) and off-board squares.
+template <class G>
+__device__ __forceinline__ bool apply_move_record(uint8_t *b, int from, int to, int promo, int rf, int rt, uint32_t r1) {
+  constexpr int NSQ = G::NSQ;
+  if (from >= NSQ || to >= NSQ) return false;  // off-board squares: undefined behaviour in the reference
+  const int turn = b[G::OFF_TURN] & 3;
+  const uint32_t piece = b[from], cap = b[to];
+  if (present(cap)) {  // RemovePiece(to), :1040-1044
+    b[to] = EMPTY;
+    if (type_of(cap) == KING) b[G::OFF_KING + color_of(cap)] = NSQ;
+  }
+  if (!present(piece)) return false;
+  b[from] = EMPTY;
+  if (type_of(piece) == KING) b[G::OFF_KING + color_of(piece)] = NSQ;
+  const uint32_t placed = promo != NO_PIECE ? mk_piece(turn, promo & 7) : piece;  // :1057-1067
+  b[to] = (uint8_t)placed;
+  if (type_of(placed) == KING) b[G::OFF_KING + color_of(placed)] = (uint8_t)to;
+  if (rf < NSQ && rt < NSQ) {  // :1070-1077
+    const uint32_t rook = b[rf];
+    b[rf] = EMPTY;
+    b[rt] = (uint8_t)rook;
+  }
+  if (r1 & 0x80) b[G::OFF_RIGHTS + turn] = (uint8_t)r1;  // :1080-1084
+  b[G::OFF_TURN] = (uint8_t)((turn + 1) & 3);             // :1088
+  return true;
+}
+
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t seed, uint64_t game, uint64_t ply) {
   uint64_t z = seed ^ (game * 0x9E3779B97F4A7C15ull) ^ (ply * 0xBF58476D1CE4E5B9ull);
   z += 0x9E3779B97F4A7C15ull;

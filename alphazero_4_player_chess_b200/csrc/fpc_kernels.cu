@@ -13,6 +13,9 @@
 
 namespace fpc {
 
+int fail(int code, const std::string &msg);
+int cuda_check(cudaError_t e, const char *what);
+
 constexpr int WARPS_PER_BLOCK = 4;  // one warp per game
 constexpr int BLOCK_THREADS = WARPS_PER_BLOCK * 32;
 
@@ -393,33 +396,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
     reinterpret_cast<uint4 *>(b)[lane] = reinterpret_cast<const uint4 *>(in + (size_t)g * G::REC)[lane];
   __syncwarp();
   if (lane == 0) {
-    constexpr int R = G::R, NSQ = G::NSQ;
+    constexpr int NSQ = G::NSQ;
     int from, to, promo = NO_PIECE, rf = NSQ, rt = NSQ;
     uint32_t r1 = 0;
-    int code = FPC_OK;
-    if (flat && (flat[g] < 0 || flat[g] >= G::ASZ)) {
-      from = to = NSQ;
-    } else if (flat) {
-      // Move(int flat_index): from = pos, to = from.Relative(...) (move.cpp:41-61)
-      const int f = flat[g];
-      const int type = f / NSQ, pos = f - type * NSQ;
-      const int row = pos / R, col = pos - row * R;
-      int dr, dc;
-      if (type < 8 * (R - 1)) {
-        const int dir = type / (R - 1), dist = type - dir * (R - 1) + 1;
-        const int d = qdelta(dir);
-        const int ur = (d + 24) / 16 - 1, uc = d - ur * 16;
-        dr = ur * dist;
-        dc = uc * dist;
-      } else {
-        int k = type - 8 * (R - 1);
-        if (k > 7) k = 7;
-        dr = kdrow(k);
-        dc = kdcol(k);
-      }
-      const int tr = row + dr, tc = col + dc;
-      from = pos;
-      to = ((unsigned)tr < (unsigned)R && (unsigned)tc < (unsigned)R) ? tr * R + tc : NSQ;
+    if (flat) {
+      decode_flat_move<G>(flat[g], from, to);
     } else {
       const uint64_t m = moves[g];
       from = (int)(m & 0xff);
@@ -429,32 +410,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
       rt = (int)((m >> 40) & 0xff);
       r1 = (uint32_t)((m >> 56) & 0xff);
     }
-    if (from >= NSQ || to >= NSQ) {
-      code = FPC_ERR_MOVE;  // off-board squares: undefined behaviour in the reference
-    } else {
-      const int turn = b[G::OFF_TURN] & 3;
-      const uint32_t piece = b[from], cap = b[to];
-      if (present(cap)) {  // RemovePiece(to), :1040-1044
-        b[to] = EMPTY;
-        if (type_of(cap) == KING) b[G::OFF_KING + color_of(cap)] = NSQ;
-      }
-      if (!present(piece)) {
-        code = FPC_ERR_MOVE;  // thrown after the capture was removed (:1046-1054)
-      } else {
-        b[from] = EMPTY;
-        if (type_of(piece) == KING) b[G::OFF_KING + color_of(piece)] = NSQ;
-        const uint32_t placed = promo != NO_PIECE ? mk_piece(turn, promo & 7) : piece;  // :1057-1067
-        b[to] = (uint8_t)placed;
-        if (type_of(placed) == KING) b[G::OFF_KING + color_of(placed)] = (uint8_t)to;
-        if (rf < NSQ && rt < NSQ) {  // :1070-1077
-          const uint32_t rook = b[rf];
-          b[rf] = EMPTY;
-          b[rt] = (uint8_t)rook;
-        }
-        if (r1 & 0x80) b[G::OFF_RIGHTS + turn] = (uint8_t)r1;  // :1080-1084
-        b[G::OFF_TURN] = (uint8_t)((turn + 1) & 3);             // :1088
-      }
-    }
+    const int code = apply_move_record<G>(b, from, to, promo, rf, rt, r1) ? FPC_OK : FPC_ERR_MOVE;
     if (err) err[g] = code;
   }
   __syncwarp();
@@ -488,11 +444,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) heuristic_kernel(const u
 
 static thread_local std::string g_err;
 
-static int fail(int code, const std::string &msg) {
+int fail(int code, const std::string &msg) {
   g_err = msg;
   return code;
 }
-static int cuda_check(cudaError_t e, const char *what) {
+int cuda_check(cudaError_t e, const char *what) {
   if (e == cudaSuccess) return FPC_OK;
   return fail(FPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }

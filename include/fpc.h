@@ -131,6 +131,65 @@ int fpc_playout_step(int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d
                      int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all,
                      float *d_mask, uint64_t *d_counters, int flags, void *stream);
 
+/* ---- batched PUCT: one warp owns one game's tree in HBM ---------------------------------------
+ *
+ * Replaces fpchess::Node (src/cpp/node.{h,cpp}) driven by MCTS.search / step / expand
+ * (src/py/mcts.py:17-89).  The tree of game g lives in slab g of caller-owned device arrays
+ * (struct-of-arrays, node_cap entries per game, children of a node contiguous and in ascending flat
+ * action index = torch.nonzero order, mcts.py:83-87).  Node 0 is the root.  Boards are materialised
+ * only for nodes that were selected as a leaf (board_cap per game; one per simulation plus the
+ * root): a child's board is its parent's board + MakeMove(Move(flat_index)) (node.cpp:87-92), made
+ * when the child is first reached instead of at expansion -- same boards, fewer copies.
+ *
+ * One simulation for all games = fpc_tree_select -> network forward on `d_planes` (PyTorch) ->
+ * fpc_tree_expand_backup.
+ */
+typedef struct fpc_tree {
+  int32_t R, n_games, node_cap, board_cap;
+  double C;               /* Node::C (alphazero.py:294) */
+  /* per node, [n_games][node_cap] */
+  int32_t *parent;        /* -1 for the root */
+  int32_t *first_child;   /* index of the first child in the same slab */
+  int32_t *n_children;    /* 0 = not expanded (Node::IsExpanded, node.cpp:14-17) */
+  int32_t *visits;        /* Node::visit_count */
+  int32_t *move_flat;     /* flat action index of Node::move_made */
+  int32_t *board_idx;     /* slot in `boards`, -1 = not materialised */
+  double *value_sum;      /* Node::value_sum */
+  float *prior;           /* Node::prior (a float32 policy value widened to double by the reference) */
+  /* per game, [n_games] */
+  int32_t *n_nodes, *n_boards;
+  int32_t *leaf;          /* node chosen by the last select, -1 = none (root dropped) */
+  int32_t *dropped;       /* 1 once a terminal leaf was reached: the root sits out the remaining
+                             simulations (mcts.py:22-23) */
+  int32_t *error;         /* bit 0 node_cap exceeded, bit 1 board_cap exceeded, bit 2 no child selectable
+                             (the reference throws, node.cpp:72-75), bit 3 index-built move failed */
+  uint8_t *boards;        /* [n_games][board_cap][record] */
+  /* the leaf batch: input of the rules kernel and of the network */
+  uint8_t *leaf_boards;   /* [n_games][record] */
+  int32_t *leaf_flat;     /* [n_games][FPC_MAX_MOVES] legal flat indices of the leaf, ascending */
+  int32_t *leaf_counts;   /* [n_games] */
+  int32_t *leaf_status;   /* [n_games] FPC_STATUS_* of the leaf */
+  int32_t *k;             /* [n_games] quarter turns the leaf's planes were rotated by */
+} fpc_tree;
+
+/* Roots: node 0 of every game = d_root_boards[g], visit_count 1 (mcts.py:30), no children. */
+int fpc_tree_reset(const fpc_tree *t, const uint8_t *d_root_boards, void *stream);
+
+/* Node::ChooseLeaf (node.cpp:19-47) for every live game: descend with Node::SelectChild
+ * (node.cpp:49-78: argmax of Q + C*sqrt(ln(sqrt(N))/(1+n))*P in double, first maximum wins),
+ * materialise the leaf's board, run the rules kernel on the leaf batch (legal moves + GetGameResult)
+ * and encode it into d_planes [n_games][24][R][R] (Board::GetEncodedStates).  batch_rotation != 0
+ * reproduces the reference: every leaf is rotated by the colour of the first live leaf
+ * (src/cpp/board.cpp:354-355); 0 rotates each leaf by its own side to move. */
+int fpc_tree_select(const fpc_tree *t, int batch_rotation, float *d_planes, void *stream);
+
+/* MCTS.step after the network (mcts.py:66-79) + MCTS.expand (mcts.py:82-89) for every game with a
+ * leaf: terminal leaf -> Backpropagate(0 | -1) and drop the root (node.cpp:33-43); otherwise
+ * softmax(d_logits[g]) -> ParseActionspace (rotate back by the leaf's k) -> * legal mask ->
+ * renormalise -> Node::BackpropagateNodes(value) -> one child per non-zero prior (visit_count 1,
+ * node.h:28).  d_logits [n_games][A*R*R] f32 in the network's (rotated) frame, d_values [n_games]. */
+int fpc_tree_expand_backup(const fpc_tree *t, const float *d_logits, const float *d_values, void *stream);
+
 /* ---- host-buffer operations (per-object calls of the binding; e2e measurement) ------------- */
 
 typedef struct fpc_ctx fpc_ctx;

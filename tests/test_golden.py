@@ -125,3 +125,25 @@ def test_known_answers_from_the_survey():
     assert flat == list(range(171, 179)) + list(range(367, 375)) + [20962, 20967, 21354, 21359]
     enc = o14.encode(rec[None], 0)[0]
     assert enc.sum(axis=(1, 2)).astype(int).tolist() == [2, 2, 2, 1, 1, 8] * 4
+
+
+@pytest.mark.parametrize("R", [8, 14])
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_mcts_fixtures(R, case):
+    """The MCTS restatement (oracle/mcts_port.py) against the reference's own MCTS.search run on the
+    reference binding with the stand-in network: identical root children and visit counts."""
+    from oracle.mcts_port import search
+    from tests.golden.fake_net import FakeNet
+    z = load(f"mcts_R{R}.npz")
+    o = oracle_for(R)
+    roots = z[f"{case}_roots"]
+    net = FakeNet(R)
+    trees = search(o, net, roots, 3, int(z[f"{case}_sims"]), batch_rotation=True)
+    off = z[f"{case}_child_off"]
+    for gi, t in enumerate(trees):
+        ch = t.children[0]
+        assert [t.move_flat[c] for c in ch] == z[f"{case}_child_flat"][off[gi]: off[gi + 1]].tolist(), gi
+        assert [t.visits[c] for c in ch] == z[f"{case}_child_visits"][off[gi]: off[gi + 1]].tolist(), gi
+        assert t.visits[0] == int(z[f"{case}_root_visits"][gi])
+        assert len(t.parent) == int(z[f"{case}_n_nodes"][gi])
+    assert net.calls == int(z[f"{case}_nn_calls"]) and net.positions == int(z[f"{case}_nn_positions"])

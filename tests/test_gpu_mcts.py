@@ -1,0 +1,101 @@
+"""-m gpu: the batched PUCT kernels (fpc_tree_* through the C-ABI) against (1) the golden fixtures
+produced by the reference's own MCTS.search and (2) the MCTS restatement oracle, node by node.
+
+Integer state (tree shape, moves, visit counts) and the double value sums must be bit-exact.  Priors are
+f32 softmax outputs: the kernel's fused softmax -> un-rotate -> mask -> renormalise differs from torch's
+op-by-op f32 arithmetic by rounding only; tolerance rtol 2e-6."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from alphazero_4_player_chess_b200.fen import start_record
+from alphazero_4_player_chess_b200.geometry import GEOMETRIES
+from alphazero_4_player_chess_b200.mcts import BatchedMCTS
+from oracle.mcts_port import search as oracle_search
+from tests.golden.fake_net import FakeNet
+from tests.util import mixed_positions, oracle_for
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PRIOR_RTOL = 2e-6
+
+
+def run_gpu(R, roots, sims, batch_rotation, C=3):
+    net = FakeNet(R, device="cuda")
+    m = BatchedMCTS(R, len(roots), net, {"C": C, "num_searches": sims}, batch_rotation=batch_rotation)
+    m.search(torch.from_numpy(np.ascontiguousarray(roots)))
+    torch.cuda.synchronize()
+    m.check_errors()
+    return m
+
+
+@pytest.mark.parametrize("R", [8, 14])
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_against_reference_mcts_fixtures(R, case):
+    z = np.load(os.path.join(GOLDEN, f"mcts_R{R}.npz"))
+    roots = z[f"{case}_roots"]
+    m = run_gpu(R, roots, int(z[f"{case}_sims"]), batch_rotation=True)
+    flat, visits, _, cnt = (t.cpu().numpy() for t in m.root_children())
+    off = z[f"{case}_child_off"]
+    for g in range(len(roots)):
+        n = off[g + 1] - off[g]
+        assert cnt[g] == n
+        assert flat[g, :n].tolist() == z[f"{case}_child_flat"][off[g]: off[g + 1]].tolist(), g
+        assert visits[g, :n].tolist() == z[f"{case}_child_visits"][off[g]: off[g + 1]].tolist(), g
+    assert m.visits[:, 0].cpu().numpy().tolist() == z[f"{case}_root_visits"].tolist()
+    assert m.n_nodes.cpu().numpy().tolist() == z[f"{case}_n_nodes"].tolist()
+
+
+@pytest.mark.parametrize("name,R,n_games,sims", [("STANDARD", 14, 24, 48), ("EIGHT_SIMPLE", 8, 32, 80), ("TEN", 10, 16, 40)])
+@pytest.mark.parametrize("batch_rotation", [True, False])
+def test_whole_trees_match_the_oracle(name, R, n_games, sims, batch_rotation):
+    g = GEOMETRIES[R]
+    o = oracle_for(R)
+    pool = mixed_positions(name, 600)
+    # late positions: short games at 8x8 put terminal leaves (root dropping) inside the search horizon
+    roots = np.ascontiguousarray(pool[len(pool) // 3:: max(1, len(pool) // (2 * n_games))][:n_games])
+    roots = np.stack([r for r in roots if o.game_result(r)[0] == 0])
+    trees = oracle_search(o, FakeNet(R), roots, 3, sims, batch_rotation=batch_rotation)
+    m = run_gpu(R, roots, sims, batch_rotation)
+    n_nodes = m.n_nodes.cpu().numpy()
+    parent, move_flat, visits = m.parent.cpu().numpy(), m.move_flat.cpu().numpy(), m.visits.cpu().numpy()
+    value_sum, prior = m.value_sum.cpu().numpy(), m.prior.cpu().numpy()
+    first_child, n_children = m.first_child.cpu().numpy(), m.n_children.cpu().numpy()
+    dropped = m.dropped.cpu().numpy()
+    n_dropped = 0
+    for gi, t in enumerate(trees):
+        nn = len(t.parent)
+        assert n_nodes[gi] == nn, gi
+        assert parent[gi, :nn].tolist() == t.parent
+        assert move_flat[gi, :nn].tolist() == t.move_flat
+        assert visits[gi, :nn].tolist() == t.visits
+        assert value_sum[gi, :nn].tolist() == t.value_sum  # doubles, bit-exact
+        np.testing.assert_allclose(prior[gi, :nn], np.array(t.prior), rtol=PRIOR_RTOL, atol=0)
+        for node in range(nn):
+            ch = t.children[node]
+            assert n_children[gi, node] == len(ch)
+            if ch:
+                assert first_child[gi, node] == ch[0] and ch == list(range(ch[0], ch[0] + len(ch)))
+        n_dropped += int(dropped[gi])
+    print(f"{name} rot={batch_rotation}: {len(trees)} games, {int(n_nodes.sum())} nodes, {n_dropped} dropped roots")
+
+
+def test_action_probs_and_capacity_errors():
+    R = 8
+    roots = np.stack([start_record("EIGHT_SIMPLE")] * 4)
+    m = run_gpu(R, roots, 30, batch_rotation=False)
+    probs = m.action_probs()
+    flat, visits, _, cnt = m.root_children()
+    assert torch.allclose(probs.sum(dim=1), torch.ones(4, device="cuda"))
+    g0 = probs[0].cpu().numpy()
+    n = int(cnt[0])
+    want = visits[0, :n].float().cpu().numpy()
+    assert np.allclose(g0[flat[0, :n].cpu().numpy()], want / want.sum())
+    # a node arena that is too small is reported, not overrun
+    small = BatchedMCTS(R, 4, FakeNet(R, device="cuda"), {"C": 3, "num_searches": 30}, node_cap=40)
+    small.search(torch.from_numpy(roots))
+    torch.cuda.synchronize()
+    assert int(small.error.max().item()) & 1
+    assert int(small.n_nodes.max().item()) <= 40
