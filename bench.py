@@ -213,9 +213,11 @@ def run_ours(args) -> None:
 
     L = _lib.lib()
     start = start_record("STANDARD", castling=True)
+    from alphazero_4_player_chess_b200.shard import Shard
+    shard = Shard(rank, world, N_GAMES)  # games are independent: no data-path collective
     env = BatchedEnv(R, N_GAMES, device=f"cuda:{local}")
-    env.reset_playout(start, first_game=rank * N_GAMES)
-    stride = world * N_GAMES
+    env.reset_playout(start, first_game=shard.first_game)
+    stride = shard.game_stride
 
     def step():
         env.playout_step(seed=SEED, max_plies=MAX_PLIES, game_stride=stride, planes=True, mask=True, k=-1,
@@ -340,9 +342,61 @@ def run_ours(args) -> None:
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg()
+        if world == 1 and not args.no_mcts:
+            del env
+            torch.cuda.empty_cache()
+            out["mcts"] = mcts_leg(rank, world, local)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def mcts_leg(rank: int, world: int, local: int, n_games: int = 1024, sims: int = 48) -> dict:
+    """configs[3] (batched PUCT self-play search): n_games x sims simulations with a random-init ResNet
+    10 x 128 of the reference architecture in PyTorch (bf16).  A bounded sample of the 400-sim
+    search so that the default run stays short; sims/s is per simulation and does not depend on the count."""
+    import torch
+
+    from alphazero_4_player_chess_b200.fen import start_record
+    from alphazero_4_player_chess_b200.mcts import BatchedMCTS
+    from alphazero_4_player_chess_b200.net import InferenceNet, PolicyValueNet
+
+    torch.manual_seed(0)
+    net = InferenceNet(PolicyValueNet(R, 10, 128, device=f"cuda:{local}"))
+    m = BatchedMCTS(R, n_games, net, {"C": 3, "num_searches": sims}, device=f"cuda:{local}")
+    roots = torch.from_numpy(start_record("STANDARD")).unsqueeze(0).repeat(n_games, 1)
+    m.args["num_searches"] = 4
+    m.search(roots)  # warm-up (cuDNN autotune, allocator)
+    m.args["num_searches"] = sims
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    m.search(roots)
+    e1.record()
+    torch.cuda.synchronize()
+    total_ms = e0.elapsed_time(e1)
+    m.check_errors()
+    # the tree kernels alone: same loop with the network replaced by fixed outputs
+    logits = torch.randn((n_games, m.geom.action_space_size), device=m.device)
+    values = torch.zeros(n_games, device=m.device)
+    m.reset(roots)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(sims):
+        m.select()
+        m.expand_backup(logits, values)
+    t1.record()
+    torch.cuda.synchronize()
+    tree_ms = t0.elapsed_time(t1)
+    return {"metric": "MCTS sims/sec", "value": n_games * sims / (total_ms * 1e-3), "unit": "sims/s",
+            "games": n_games, "sims_per_search": sims, "ms_per_sim_batch": total_ms / sims,
+            "tree_kernels_only": {"value": n_games * sims / (tree_ms * 1e-3), "unit": "sims/s",
+                                  "ms_per_sim_batch": tree_ms / sims},
+            "network_share": max(0.0, 1.0 - tree_ms / total_ms),
+            "nodes": int(m.n_nodes.sum().item()),
+            "config": "configs[3]: batched PUCT, 14x14 STANDARD roots, C=3, random-init ResNet 10x128 (reference "
+                      "architecture incl. the 23,520^2 policy Linear) in PyTorch bf16; bounded sample of "
+                      "the 400-sim search"}
 
 
 def main():
@@ -352,6 +406,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mcts", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
