@@ -125,60 +125,93 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-def run_reference(args) -> None:
-    """The reference's own CPU implementation of the path (oracle/_ref), all host threads."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def engine_only_rate(seconds: float) -> dict | None:
+    """B1: the unmodified reference RULES ENGINE alone (oracle/_ref/libref_engine_R14.so), one
+    C++ thread per host core: GetGameResult + GetPseudoLegalMoves2 + make/IsKingInCheck/undo + MakeMove.
+    No tensors are produced, so this is a lower bound on the reference's cost for the path."""
     from alphazero_4_player_chess_b200.fen import start_record
     from oracle import ref_engine
     if not ref_engine.available(R):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_engine_R14.so not built"}))
-        return
-    eng = ref_engine.RefEngine(R)
+        return None
     threads = host_threads()
+    eng = ref_engine.RefEngine(R)
     env = ref_engine.RefEnv(eng, start_record("STANDARD", castling=True), N_GAMES, SEED, n_threads=threads,
                             max_plies=MAX_PLIES)
-    for _ in range(args.warmup):
+    env.step()
+    steps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
         env.step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        env.step()
+        steps += 1
     dt = time.perf_counter() - t0
     env.close()
-    value = args.steps * N_GAMES / dt
-    sample = (f"{args.steps} steps x {N_GAMES} resident games through chess::Board (GetGameResult + "
-              f"GetPseudoLegalMoves2 + make/IsKingInCheck/undo + MakeMove), engine path B1: no planes/mask "
-              f"tensors are written (favours the reference)")
+    return {"value": steps * N_GAMES / dt, "unit": UNIT, "cores": threads,
+            "sample": f"{steps} steps x {N_GAMES} games, {dt:.1f} s, rules engine only (no planes / mask tensors)"}
+
+
+def reference_full_path(steps: int, warmup: int, n_games: int) -> dict | None:
+    """B2: the reference's own implementation of the WHOLE path -- engine + GetEncodedStates +
+    legal mask -- through its own pybind module, one process per host core (oracle/ref_binding_env.py)."""
+    from alphazero_4_player_chess_b200.fen import start_record
+    from oracle import ref_binding_env
+    if not ref_binding_env.available(R):
+        return None
+    threads = host_threads()
+    # the Python path of the reference builds boards without castling rights (fen_parser.py:137-140,170)
+    r = ref_binding_env.run(R, start_record("STANDARD", castling=False), n_games, steps, warmup, threads,
+                            max_plies=MAX_PLIES, seed=SEED)
+    return {"value": r["positions_per_s"], "unit": UNIT, "cores": r["procs"], "seconds": r["seconds"],
+            "positions": r["positions"]}
+
+
+def run_reference(args) -> None:
+    """The reference's own CPU implementation of the path, all host cores: `value` is the full path
+    (movegen + legal filter + make + planes + mask through the reference binding, like our arm);
+    `engine_only` is its rules engine alone."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # each step = one ply of a bounded sample of the resident games (the full 4,096 would take ~70 ms a step
+    # on 16 cores; 1,024 keeps a --steps 400 run within a minute)
+    sample_games = 1024
+    full = reference_full_path(args.steps, max(args.warmup, 1), sample_games)
+    eng = engine_only_rate(6.0)
+    if full is None and eng is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (no /root/reference here)"}))
+        return
+    kind_note = ("reference pybind module alphazero_cpp (unmodified, oracle/_ref/binding_R14), one process per core: "
+                 "GetGameResult + GetLegalMoves + TakeAction per game, GetEncodedStates + legal mask per batch, CPU "
+                 "tensors")
+    if full is None:
+        full = dict(eng)
+        kind_note = "rules engine only (binding not built): " + eng["sample"]
+    value = full["value"]
+    sample = f"{args.steps} steps x {sample_games} of the {N_GAMES} resident games; {kind_note}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sample_games / value * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": full["cores"], "kind": "reference", "sample": sample},
+        "engine_only": eng,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def cpu_baseline_leg(seconds: float = 12.0) -> dict:
+def cpu_baseline_leg() -> dict:
+    """Reported beside our number: the reference's full path on a bounded sample (~15 s), plus its rules
+    engine alone; falls back to the single-thread oracle port where oracle/_ref does not exist."""
     from alphazero_4_player_chess_b200.fen import start_record
-    from oracle import ref_engine
     threads = host_threads()
-    if ref_engine.available(R):
-        eng = ref_engine.RefEngine(R)
-        env = ref_engine.RefEnv(eng, start_record("STANDARD", castling=True), N_GAMES, SEED, n_threads=threads,
-                                max_plies=MAX_PLIES)
-        env.step()
-        steps, t0 = 0, time.perf_counter()
-        while time.perf_counter() - t0 < seconds:
-            env.step()
-            steps += 1
-        dt = time.perf_counter() - t0
-        env.close()
-        return {"value": steps * N_GAMES / dt, "unit": UNIT, "cores": threads, "kind": "reference",
-                "sample": f"{steps} steps x {N_GAMES} games of the same workload through the unmodified reference "
-                          f"engine (oracle/_ref), {dt:.1f} s; engine path only, no planes/mask written"}
+    eng = engine_only_rate(5.0)
+    full = reference_full_path(steps=12, warmup=2, n_games=1024)
+    if full is not None:
+        return {"value": full["value"], "unit": UNIT, "cores": full["cores"], "kind": "reference",
+                "sample": f"12 plies x 1024 games ({full['positions']} positions, {full['seconds']:.1f} s) through the "
+                          "unmodified reference binding: engine + GetEncodedStates + legal mask on CPU tensors, one "
+                          "process per core", "engine_only": eng}
+    if eng is not None:
+        return {"value": eng["value"], "unit": UNIT, "cores": threads, "kind": "reference", "sample": eng["sample"]}
     from oracle.port import Oracle
     o = Oracle(R, 3)
     t0 = time.perf_counter()
