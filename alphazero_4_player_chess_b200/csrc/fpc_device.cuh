@@ -29,6 +29,8 @@ struct Geo {
   static constexpr int SSZ = 24 * NSQ;            // state_space_size
   static constexpr int MASK_WORDS = (ASZ + 31) / 32;
   static constexpr int PLANE_WORDS = (SSZ + 31) / 32;
+  // bit sets are moved 16 bytes at a time: per-game strides are whole uint4s
+  static constexpr int MASK_STRIDE = (MASK_WORDS + 3) / 4 * 4, PLANE_STRIDE = (PLANE_WORDS + 3) / 4 * 4;
   static_assert(R_ <= 14, "mailbox is 16x16 with a one-cell border");
   static_assert(ASZ % 4 == 0 && SSZ % 4 == 0, "float4 streaming of the dense outputs");
 
@@ -62,8 +64,8 @@ __device__ __forceinline__ int kdrow(int k) { return (int)(int8_t)((0x01FF'02FE'
 // Per-warp shared-memory scratch.
 template <class G>
 struct alignas(16) WarpScratch {
-  uint32_t mask_bits[G::MASK_WORDS + (4 - G::MASK_WORDS % 4) % 4];   // legal-move mask, 1 bit per action
-  uint32_t plane_bits[G::PLANE_WORDS + (4 - G::PLANE_WORDS % 4) % 4];  // input planes, 1 bit per cell
+  uint32_t mask_bits[G::MASK_STRIDE];    // legal-move mask, 1 bit per action
+  uint32_t plane_bits[G::PLANE_STRIDE];  // input planes, 1 bit per cell
   uint32_t moves[MAX_MOVES + 4];  // compact moves: key<<14 | castle<<8 | to_mb, key = flat*8 + promo
   uint8_t mb[256];                // mailbox board
   uint8_t rec[256];               // raw record staging (in and out)

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -57,6 +58,23 @@ struct ObserveParams {
     if (rc_ != FPC_OK) return rc_;                 \
   } while (0)
 
+// Record <-> mailbox without per-byte index arithmetic: lane l < 2R owns half a row (row l/2, columns
+// (l&1)*H .. +H, H = ceil(R/2)), so row / column / legality are lane constants and the column loop unrolls.
+template <class G>
+struct HalfRow {
+  static constexpr int H = (G::R + 1) / 2;
+  int row, c0;
+  bool active, corner_row;
+  __device__ __forceinline__ explicit HalfRow(int lane)
+      : row(lane >> 1), c0((lane & 1) * H), active(lane < 2 * G::R),
+        corner_row((lane >> 1) < G::IA || (lane >> 1) > G::R - 1 - G::IA) {}
+  // is column c0 + j an on-board square of this lane's row?
+  __device__ __forceinline__ bool on_board(int j) const {
+    const int c = c0 + j;
+    return active && c < G::R && !(corner_row && (c < G::IA || c > G::R - 1 - G::IA));
+  }
+};
+
 template <class G>
 __device__ __forceinline__ void load_record(WarpScratch<G> &s, const uint8_t *rec_g, int lane) {
   // mailbox <- WALL; record -> staging (coalesced 16-byte loads: the record is contiguous)
@@ -67,33 +85,28 @@ __device__ __forceinline__ void load_record(WarpScratch<G> &s, const uint8_t *re
   __syncwarp();
   if (lane < 4) s.rights[lane] = s.rec[G::OFF_RIGHTS + lane];
   if (lane == 0) s.turn = s.rec[G::OFF_TURN] & 3;
-  for (int sq = lane; sq < G::NSQ; sq += 32) {
-    const int r = sq / G::R, c = sq - r * G::R;
-    if (G::legal(r, c)) {
-      const uint32_t p = s.rec[sq];
-      s.mb[G::mb(r, c)] = (uint8_t)p;
-      if (present(p) && type_of(p) == KING) s.king[color_of(p)] = (uint8_t)G::mb(r, c);
-    }
-  }
-  __syncwarp();
 }
 
 template <class G>
 __device__ __forceinline__ void store_record(WarpScratch<G> &s, uint8_t *rec_g, int lane) {
-  for (int sq = lane; sq < G::REC; sq += 32) {
+  const HalfRow<G> hr(lane);
+#pragma unroll
+  for (int j = 0; j < HalfRow<G>::H; ++j) {
+    const int c = hr.c0 + j;
+    if (hr.active && c < G::R) s.rec[hr.row * G::R + c] = hr.on_board(j) ? s.mb[G::mb(hr.row, c)] : (uint8_t)EMPTY;
+  }
+  if (lane < G::REC - G::NSQ) {
+    const int i = G::NSQ + lane;
     uint32_t v = 0;
-    if (sq < G::NSQ) {
-      const int r = sq / G::R, c = sq - r * G::R;
-      v = G::legal(r, c) ? s.mb[G::mb(r, c)] : EMPTY;
-    } else if (sq == G::OFF_TURN) {
+    if (i == G::OFF_TURN) {
       v = s.turn;
-    } else if (sq < G::OFF_KING) {
-      v = s.rights[sq - G::OFF_RIGHTS];
-    } else if (sq < G::OFF_KING + 4) {
-      const int k = s.king[sq - G::OFF_KING];
+    } else if (i < G::OFF_KING) {
+      v = s.rights[i - G::OFF_RIGHTS];
+    } else if (i < G::OFF_KING + 4) {
+      const int k = s.king[i - G::OFF_KING];
       v = k == NO_SQ ? G::NSQ : G::sq_of_mb(k);
     }
-    s.rec[sq] = (uint8_t)v;
+    s.rec[i] = (uint8_t)v;
   }
   __syncwarp();
   if (lane < G::REC / 16) reinterpret_cast<uint4 *>(rec_g)[lane] = reinterpret_cast<const uint4 *>(s.rec)[lane];
@@ -112,51 +125,52 @@ __global__ void __launch_bounds__(BLOCK_THREADS) rules_kernel(const __grid_const
   const unsigned lt_mask = (1u << lane) - 1u;
 
   if (P.mask_bits)
-    for (int i = lane; i < G::MASK_WORDS; i += 32) s.mask_bits[i] = 0;
+    for (int i = lane; i < G::MASK_STRIDE / 4; i += 32) reinterpret_cast<uint4 *>(s.mask_bits)[i] = make_uint4(0, 0, 0, 0);
   if (P.plane_bits)
-    for (int i = lane; i < G::PLANE_WORDS; i += 32) s.plane_bits[i] = 0;
+    for (int i = lane; i < G::PLANE_STRIDE / 4; i += 32) reinterpret_cast<uint4 *>(s.plane_bits)[i] = make_uint4(0, 0, 0, 0);
   // playout bookkeeping is read up front: with zero-copy host buffers each load is a PCIe round trip
   const uint64_t game_id = P.playout ? P.game[g] : 0;
   const int ply = P.playout ? P.ply[g] : 0;
   load_record<G>(s, P.boards_in + (size_t)g * G::REC, lane);
+  __syncwarp();
   const int turn = s.turn;
 
-  // ---- piece scan: mover's piece list + input-plane bits (src/cpp/board.cpp:318-344) -----
+  // ---- unpack into the mailbox + piece scan: king squares, the mover's piece list, the
+  //      input-plane bits (src/cpp/board.cpp:318-344) ------------------------------------------
   int rot = 0;
   if (P.plane_bits) {
     rot = P.k ? P.k[g] : (P.k_all < 0 ? turn : P.k_all);
     rot &= 3;
   }
   int np = 0;
-  for (int base = 0; base < G::NSQ; base += 32) {
-    const int sq = base + lane;
-    uint32_t p = EMPTY;
-    int r = 0, c = 0;
-    if (sq < G::NSQ) {
-      r = sq / G::R;
-      c = sq - r * G::R;
-      if (G::legal(r, c)) p = s.mb[G::mb(r, c)];
-    }
-    const bool mine = present(p) && color_of(p) == turn;
-    const unsigned b = __ballot_sync(FULL, mine);
-    if (mine) {
-      const int idx = np + __popc(b & lt_mask);
-      if (idx < 64) s.plist[idx] = (uint8_t)G::mb(r, c);
-    }
-    np += __popc(b);
-    if (P.plane_bits && present(p)) {
-      // ch = ((color - turn) mod 4)*6 + type - 1, -1 wrapping to 23 (src/cpp/board.cpp:336)
-      int ch = ((color_of(p) - turn) & 3) * 6 + type_of(p) - 1;
-      if (ch < 0) ch += 24;
-      // torch.rot90(k) on the last two dims: one quarter turn sends (r,c) -> (R-1-c, r)
-      int rr = r, cc = c;
-      for (int t = 0; t < rot; ++t) {
-        const int nr = G::R - 1 - cc;
-        cc = rr;
-        rr = nr;
+  {
+    const HalfRow<G> hr(lane);
+#pragma unroll
+    for (int j = 0; j < HalfRow<G>::H; ++j) {
+      const int r = hr.row, c = hr.c0 + j;
+      uint32_t p = EMPTY;
+      if (hr.on_board(j)) {
+        p = s.rec[r * G::R + c];
+        s.mb[G::mb(r, c)] = (uint8_t)p;
+        if (present(p) && type_of(p) == KING) s.king[color_of(p)] = (uint8_t)G::mb(r, c);
       }
-      const int bit = ch * G::NSQ + rr * G::R + cc;
-      atomicOr(&s.plane_bits[bit >> 5], 1u << (bit & 31));
+      const bool mine = present(p) && color_of(p) == turn;
+      const unsigned b = __ballot_sync(FULL, mine);
+      if (mine) {
+        const int idx = np + __popc(b & lt_mask);
+        if (idx < 64) s.plist[idx] = (uint8_t)G::mb(r, c);
+      }
+      np += __popc(b);
+      if (P.plane_bits && present(p)) {
+        // ch = ((color - turn) mod 4)*6 + type - 1, -1 wrapping to 23 (src/cpp/board.cpp:336)
+        int ch = ((color_of(p) - turn) & 3) * 6 + type_of(p) - 1;
+        if (ch < 0) ch += 24;
+        // torch.rot90(k) on the last two dims: one quarter turn sends (r,c) -> (R-1-c, r)
+        const int rr = rot == 0 ? r : (rot == 1 ? G::R - 1 - c : (rot == 2 ? G::R - 1 - r : c));
+        const int cc = rot == 0 ? c : (rot == 1 ? r : (rot == 2 ? G::R - 1 - c : G::R - 1 - r));
+        const int bit = ch * G::NSQ + rr * G::R + cc;
+        atomicOr(&s.plane_bits[bit >> 5], 1u << (bit & 31));
+      }
     }
   }
   if (np > 64) np = 64;
@@ -283,9 +297,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) rules_kernel(const __grid_const
   // ---- bit sets of the dense outputs (coalesced; expand_kernel turns them into f32) --------------
   __syncwarp();
   if (P.plane_bits)
-    for (int i = lane; i < G::PLANE_WORDS; i += 32) P.plane_bits[(size_t)g * G::PLANE_WORDS + i] = s.plane_bits[i];
+    for (int i = lane; i < G::PLANE_STRIDE / 4; i += 32)
+      reinterpret_cast<uint4 *>(P.plane_bits + (size_t)g * G::PLANE_STRIDE)[i] = reinterpret_cast<const uint4 *>(s.plane_bits)[i];
   if (P.mask_bits)
-    for (int i = lane; i < G::MASK_WORDS; i += 32) P.mask_bits[(size_t)g * G::MASK_WORDS + i] = s.mask_bits[i];
+    for (int i = lane; i < G::MASK_STRIDE / 4; i += 32)
+      reinterpret_cast<uint4 *>(P.mask_bits + (size_t)g * G::MASK_STRIDE)[i] = reinterpret_cast<const uint4 *>(s.mask_bits)[i];
 
   // ---- playout: play the chosen move or re-seed the slot ------------------------------------
   if (P.playout) {
@@ -337,23 +353,23 @@ __global__ void __launch_bounds__(BLOCK_THREADS) rules_kernel(const __grid_const
 // floats_per_game floats).  A warp takes 32 words of one game per iteration with one coalesced
 // load, hands them round with shuffles and issues 8 store instructions of 512 contiguous bytes.
 // Pure streaming: no shared memory, one pass, HBM-write bound.
-constexpr int EXPAND_THREADS = 256;
-constexpr int EXPAND_ITERS = 2;  // 32-word groups per warp
+constexpr int EXPAND_THREADS = 128;
+constexpr int EXPAND_ITERS = 1;  // 32-word groups per warp (finer CTAs stream better: tools/sweep.sh)
 
 struct ExpandHalf {
   const uint32_t *bits;  // [n][words]
   float *out;            // [n][floats]
-  int words, floats, groups;  // per game; groups = ceil(words / 32)
+  int words, stride, floats, groups;  // per game: words used, words allocated, floats, ceil(words / 32)
 };
 
-__global__ void __launch_bounds__(EXPAND_THREADS)
-    expand_kernel(const __grid_constant__ ExpandHalf A, const __grid_constant__ ExpandHalf B, int n) {
+__global__ void __launch_bounds__(512)
+    expand_kernel(const __grid_constant__ ExpandHalf A, const __grid_constant__ ExpandHalf B, int n, int iters) {
   const int lane = threadIdx.x & 31;
-  const unsigned long long warp = (unsigned long long)blockIdx.x * (EXPAND_THREADS / 32) + (threadIdx.x >> 5);
+  const unsigned long long warp = (unsigned long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const unsigned long long total_a = (unsigned long long)n * A.groups, total_b = (unsigned long long)n * B.groups;
 #pragma unroll 1
-  for (int it = 0; it < EXPAND_ITERS; ++it) {
-    unsigned long long grp = warp * EXPAND_ITERS + it;
+  for (int it = 0; it < iters; ++it) {
+    unsigned long long grp = warp * iters + it;
     const ExpandHalf *H = &A;
     if (grp >= total_a) {
       grp -= total_a;
@@ -362,7 +378,7 @@ __global__ void __launch_bounds__(EXPAND_THREADS)
     }
     const unsigned long long game = grp / H->groups;
     const int w0 = (int)(grp - game * H->groups) * 32;
-    const uint32_t mine = w0 + lane < H->words ? __ldg(H->bits + game * H->words + w0 + lane) : 0u;
+    const uint32_t mine = w0 + lane < H->words ? __ldg(H->bits + game * H->stride + w0 + lane) : 0u;
     float4 *dst = reinterpret_cast<float4 *>(H->out + game * H->floats);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -521,7 +537,7 @@ static int launch_observe(ObserveParams p, DenseOut d, cudaStream_t st, F after_
   if (dense) {
     if ((reinterpret_cast<uintptr_t>(d.planes) | reinterpret_cast<uintptr_t>(d.mask)) & 15)
       return fail(FPC_ERR_ARG, "planes / mask must be 16-byte aligned");
-    const size_t pw = (size_t)p.n * G::PLANE_WORDS, mw = (size_t)p.n * G::MASK_WORDS;
+    const size_t pw = (size_t)p.n * G::PLANE_STRIDE, mw = (size_t)p.n * G::MASK_STRIDE;
     int rc = side_state(&S, pw + mw, st);
     if (rc != FPC_OK) return rc;
     b = S->parity;
@@ -548,12 +564,14 @@ static int launch_observe(ObserveParams p, DenseOut d, cudaStream_t st, F after_
   if (rc != FPC_OK) return rc;
   {
     CK(cudaStreamWaitEvent(S->side, S->rules_done[b], 0));
-    ExpandHalf A{p.plane_bits, d.planes, G::PLANE_WORDS, G::SSZ, d.planes ? (G::PLANE_WORDS + 31) / 32 : 0};
-    ExpandHalf B{p.mask_bits, d.mask, G::MASK_WORDS, G::ASZ, d.mask ? (G::MASK_WORDS + 31) / 32 : 0};
+    ExpandHalf A{p.plane_bits, d.planes, G::PLANE_WORDS, G::PLANE_STRIDE, G::SSZ, d.planes ? (G::PLANE_WORDS + 31) / 32 : 0};
+    ExpandHalf B{p.mask_bits, d.mask, G::MASK_WORDS, G::MASK_STRIDE, G::ASZ, d.mask ? (G::MASK_WORDS + 31) / 32 : 0};
     const unsigned long long groups = (unsigned long long)p.n * (A.groups + B.groups);
-    const unsigned long long warps = (groups + EXPAND_ITERS - 1) / EXPAND_ITERS;
-    const unsigned long long grid = (warps + EXPAND_THREADS / 32 - 1) / (EXPAND_THREADS / 32);
-    expand_kernel<<<(unsigned)grid, EXPAND_THREADS, 0, S->side>>>(A, B, p.n);
+    static const int iters = getenv("FPC_EXPAND_ITERS") ? atoi(getenv("FPC_EXPAND_ITERS")) : EXPAND_ITERS;
+    static const int threads = getenv("FPC_EXPAND_THREADS") ? atoi(getenv("FPC_EXPAND_THREADS")) : EXPAND_THREADS;
+    const unsigned long long warps = (groups + iters - 1) / iters;
+    const unsigned long long grid = (warps + threads / 32 - 1) / (threads / 32);
+    expand_kernel<<<(unsigned)grid, threads, 0, S->side>>>(A, B, p.n, iters);
     CK(cudaGetLastError());
     CK(cudaEventRecord(S->expand_done[b], S->side));
     S->expand_recorded[b] = true;
