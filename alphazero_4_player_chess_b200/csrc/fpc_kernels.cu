@@ -116,7 +116,7 @@ __device__ __forceinline__ void store_record(WarpScratch<G> &s, uint8_t *rec_g, 
 // and (playout) the move choice and make-move.  It touches only the board store and compact
 // per-game outputs.
 template <class G>
-__global__ void __launch_bounds__(BLOCK_THREADS) rules_kernel(const __grid_constant__ ObserveParams P) {
+__global__ void __launch_bounds__(BLOCK_THREADS, 12) rules_kernel(const __grid_constant__ ObserveParams P) {
   __shared__ WarpScratch<G> scratch[WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * WARPS_PER_BLOCK + wib;
