@@ -380,20 +380,23 @@ __global__ void __launch_bounds__(512)
     const int w0 = (int)(grp - game * H->groups) * 32;
     const uint32_t mine = w0 + lane < H->words ? __ldg(H->bits + game * H->stride + w0 + lane) : 0u;
     float4 *dst = reinterpret_cast<float4 *>(H->out + game * H->floats);
+    // almost every word is zero (~40 ones among 4,704 cells, ~19 among 23,520): a store whose four
+    // words are all zero needs no shuffle and no bit arithmetic -- warp-uniform test on one ballot
+    const unsigned nz = __ballot_sync(FULL, mine != 0u);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       // store j, lane l: float4 number w0*8 + j*32 + l of this game = word w0 + j*4 + l/8, nibble l%8
-      const uint32_t w = __shfl_sync(FULL, mine, j * 4 + (lane >> 3));
-      const uint32_t nib = (w >> ((lane & 7) * 4)) & 15u;
       const int f4 = w0 * 8 + j * 32 + lane;
-      if (f4 * 4 < H->floats) {
-        float4 v;
+      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if ((nz >> (j * 4)) & 15u) {
+        const uint32_t w = __shfl_sync(FULL, mine, j * 4 + (lane >> 3));
+        const uint32_t nib = (w >> ((lane & 7) * 4)) & 15u;
         v.x = (nib & 1u) ? 1.0f : 0.0f;
         v.y = (nib & 2u) ? 1.0f : 0.0f;
         v.z = (nib & 4u) ? 1.0f : 0.0f;
         v.w = (nib & 8u) ? 1.0f : 0.0f;
-        __stcs(dst + f4, v);
       }
+      if (f4 * 4 < H->floats) __stcs(dst + f4, v);
     }
   }
 }
@@ -482,7 +485,12 @@ struct SideState {
   size_t bits_words = 0;
   int parity = 0;
   int last = -1;  // buffer of the most recent expansion (fpc_join)
+  // optional CUDA-event timing of expand_kernel on its own stream (fpc_profile_enable / _read)
+  bool prof_on = false;
+  int prof_n = 0;
+  std::vector<cudaEvent_t> prof_ev;
 };
+constexpr int PROF_MAX = 4096;
 static thread_local SideState g_side[16];
 
 static int side_state(SideState **out, size_t words, cudaStream_t st) {
@@ -571,8 +579,11 @@ static int launch_observe(ObserveParams p, DenseOut d, cudaStream_t st, F after_
     static const int threads = getenv("FPC_EXPAND_THREADS") ? atoi(getenv("FPC_EXPAND_THREADS")) : EXPAND_THREADS;
     const unsigned long long warps = (groups + iters - 1) / iters;
     const unsigned long long grid = (warps + threads / 32 - 1) / (threads / 32);
+    const bool prof = S->prof_on && S->prof_n < PROF_MAX;
+    if (prof) CK(cudaEventRecord(S->prof_ev[2 * S->prof_n], S->side));
     expand_kernel<<<(unsigned)grid, threads, 0, S->side>>>(A, B, p.n, iters);
     CK(cudaGetLastError());
+    if (prof) CK(cudaEventRecord(S->prof_ev[2 * S->prof_n++ + 1], S->side));
     CK(cudaEventRecord(S->expand_done[b], S->side));
     S->expand_recorded[b] = true;
     S->last = b;
@@ -676,6 +687,35 @@ int fpc_move_flat_index(int R, uint64_t move) {
     if (dx == kKd[i][0] && dy == kKd[i][1]) plane = 8 * (R - 1) + i;
   if (plane < 0) return -1;
   return plane * R * R + (from / R) * R + from % R;
+}
+
+int fpc_profile_enable(int on) {
+  SideState *S = nullptr;
+  int rc = side_state(&S, 0, nullptr);
+  if (rc != FPC_OK) return rc;
+  if (on && S->prof_ev.empty()) {
+    S->prof_ev.resize(2 * PROF_MAX);
+    for (auto &e : S->prof_ev) CK(cudaEventCreate(&e));
+  }
+  S->prof_on = on != 0;
+  S->prof_n = 0;
+  return FPC_OK;
+}
+
+int fpc_profile_read(int *launches, double *expand_ms) {
+  SideState *S = nullptr;
+  int rc = side_state(&S, 0, nullptr);
+  if (rc != FPC_OK) return rc;
+  CK(cudaStreamSynchronize(S->side));
+  double total = 0;
+  for (int i = 0; i < S->prof_n; ++i) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, S->prof_ev[2 * i], S->prof_ev[2 * i + 1]));
+    total += ms;
+  }
+  if (launches) *launches = S->prof_n;
+  if (expand_ms) *expand_ms = total;
+  return FPC_OK;
 }
 
 int fpc_join(void *stream) {

@@ -66,6 +66,16 @@ class BatchedEnv:
             self._flat = torch.zeros((self.n, FPC_MAX_MOVES), dtype=torch.int32, device=self.device)
         return self._flat
 
+    # ---- zero-copy hand-off (DLPack) --------------------------------------------------------------
+    def dlpack(self, name: str = "planes"):
+        """DLPack capsule of a device buffer ("planes", "mask", "boards", "counts", "status", "moves", "flat"):
+        the same memory the kernels write, for any DLPack consumer (`torch.from_dlpack`, CuPy, JAX ...)."""
+        from torch.utils.dlpack import to_dlpack
+        buf = {"planes": self.planes_buffer, "mask": self.mask_buffer, "moves": self.moves_buffer,
+               "flat": self.flat_buffer, "boards": lambda: self.boards, "counts": lambda: self.counts,
+               "status": lambda: self.status}[name]()
+        return to_dlpack(buf)
+
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 

@@ -204,10 +204,10 @@ def cpu_baseline_leg() -> dict:
     from alphazero_4_player_chess_b200.fen import start_record
     threads = host_threads()
     eng = engine_only_rate(5.0)
-    full = reference_full_path(steps=12, warmup=2, n_games=1024)
+    full = reference_full_path(steps=300, warmup=3, n_games=1024)
     if full is not None:
         return {"value": full["value"], "unit": UNIT, "cores": full["cores"], "kind": "reference",
-                "sample": f"12 plies x 1024 games ({full['positions']} positions, {full['seconds']:.1f} s) through the "
+                "sample": f"300 plies x 1024 games ({full['positions']} positions, {full['seconds']:.1f} s) through the "
                           "unmodified reference binding: engine + GetEncodedStates + legal mask on CPU tensors, one "
                           "process per core", "engine_only": eng}
     if eng is not None:
@@ -266,6 +266,7 @@ def run_ours(args) -> None:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     env.counters.zero_()
+    _lib.check(L.fpc_profile_enable(1))  # CUDA events around every expand_kernel launch, on its own stream
     barrier()
     e0.record()
     for _ in range(args.steps):
@@ -275,6 +276,10 @@ def run_ours(args) -> None:
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
+    import ctypes
+    ex_n, ex_ms = ctypes.c_int(0), ctypes.c_double(0.0)
+    _lib.check(L.fpc_profile_read(ctypes.byref(ex_n), ctypes.byref(ex_ms)))
+    _lib.check(L.fpc_profile_enable(0))
 
     # rules only (movegen + legal filter + result + make, no dense tensors): the integer-bound part
     env_counters = env.counters.clone()
@@ -339,10 +344,13 @@ def run_ours(args) -> None:
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        # dominant kernel: expand_kernel, one launch per step, back to back on its stream: its average
-        # launch duration is the step time of the pipelined loop (the rules kernel hides beneath it)
+        # dominant kernel: expand_kernel (the dense f32 planes + mask, 112,896 of the 113,312 algorithmic bytes
+        # per position), one launch per step, each timed with CUDA events on the stream it runs on while the
+        # rules kernel of the next step overlaps it
         per_gpu_ms = ms_max / args.steps
-        achieved = N_GAMES * BYTES_PER_POSITION / (per_gpu_ms * 1e-3) / 1e9
+        ex_avg_ms = ex_ms.value / max(ex_n.value, 1)
+        achieved = N_GAMES * DENSE_BYTES_PER_POSITION / (ex_avg_ms * 1e-3) / 1e9 if ex_n.value else 0.0
+        step_gbs = N_GAMES * BYTES_PER_POSITION / (per_gpu_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
         if os.path.exists(tp):
@@ -362,9 +370,12 @@ def run_ours(args) -> None:
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "expand_kernel (+ rules_kernel<Geo<14,3>> overlapped)",
-                         "bytes_per_launch": N_GAMES * BYTES_PER_POSITION,
-                         "avg_launch_ms": per_gpu_ms},
+                         "kernel": "expand_kernel", "bytes_per_launch": N_GAMES * DENSE_BYTES_PER_POSITION,
+                         "avg_launch_ms": ex_avg_ms, "launches_timed": ex_n.value,
+                         "whole_step": {"bytes": N_GAMES * BYTES_PER_POSITION, "ms": per_gpu_ms, "achieved": step_gbs,
+                                        "frac": step_gbs / peak,
+                                        "note": "rules_kernel + expand_kernel pipelined; 113,312 B per position over "
+                                                "the event-timed step"}},
             "rules_only": {"value": N_GAMES / (rules_ms * 1e-3) * world, "unit": UNIT, "ms_per_step": rules_ms,
                            "note": "same step without the dense f32 tensors (movegen + legal filter + result + "
                                    "make); integer/latency bound, 416 B of board traffic per position"},
@@ -376,6 +387,7 @@ def run_ours(args) -> None:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg()
         if world == 1 and not args.no_mcts:
+            out["perft"] = perft_leg(local)
             del env
             torch.cuda.empty_cache()
             out["mcts"] = mcts_leg(rank, world, local)
@@ -430,6 +442,33 @@ def mcts_leg(rank: int, world: int, local: int, n_games: int = 1024, sims: int =
             "config": "configs[3]: batched PUCT, 14x14 STANDARD roots, C=3, random-init ResNet 10x128 (reference "
                       "architecture incl. the 23,520^2 policy Linear) in PyTorch bf16; bounded sample of "
                       "the 400-sim search"}
+
+
+def perft_leg(local: int) -> dict:
+    """configs[0]: perft from the 14x14 STANDARD start (known answers SURVEY 8c), device vs the unmodified
+    reference engine on one host core (its perft is a serial copy-make recursion)."""
+    import torch
+
+    from alphazero_4_player_chess_b200.fen import start_record
+    from alphazero_4_player_chess_b200.perft import perft
+    from oracle import ref_engine
+    root = start_record("STANDARD", castling=True)
+    want = [20, 395, 7800, 152050, 3450730]
+    perft(R, root, 3, device=f"cuda:{local}")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got = perft(R, root, 5, device=f"cuda:{local}")
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out = {"depth": 5, "counts": got, "matches_known_answers": got == want, "seconds": dt,
+           "leaves_per_s": got[-1] / dt}
+    if ref_engine.available(R):
+        eng = ref_engine.RefEngine(R)
+        t0 = time.perf_counter()
+        n4 = eng.perft(root, 4)
+        dt4 = time.perf_counter() - t0
+        out["reference_cpu"] = {"depth": 4, "count": n4, "seconds": dt4, "leaves_per_s": n4 / dt4, "cores": 1}
+    return out
 
 
 def main():

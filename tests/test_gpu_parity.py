@@ -25,31 +25,9 @@ PERFT = {  # SURVEY 8c known answers, reproduced by oracle/_ref in tests/test_or
 
 
 def gpu_perft(name, depth, castling):
+    from alphazero_4_player_chess_b200.perft import perft
     _, R = START_FENS[name]
-    L = _lib.lib()
-    frontier = torch.as_tensor(start_record(name, castling=castling)).cuda().unsqueeze(0).contiguous()
-    out = []
-    for d in range(depth):
-        n = frontier.shape[0]
-        counts = torch.zeros(n, dtype=torch.int32, device="cuda")
-        moves = torch.zeros((n, _lib.FPC_MAX_MOVES), dtype=torch.int64, device="cuda")
-        _lib.check(L.fpc_observe(R, frontier.data_ptr(), n, moves.data_ptr(), None, counts.data_ptr(), None,
-                                 None, None, -1, None, 0, None))
-        out.append(int(counts.sum().item()))
-        if d == depth - 1:
-            break
-        idx = torch.repeat_interleave(torch.arange(n, device="cuda"), counts.long())
-        start = torch.cumsum(counts.long(), 0) - counts.long()
-        within = torch.arange(idx.numel(), device="cuda") - start[idx]
-        mv = moves[idx, within].contiguous()
-        parents = frontier[idx].contiguous()
-        children = torch.empty_like(parents)
-        err = torch.zeros(idx.numel(), dtype=torch.int32, device="cuda")
-        _lib.check(L.fpc_make_moves(R, parents.data_ptr(), mv.data_ptr(), idx.numel(), children.data_ptr(),
-                                    err.data_ptr(), None))
-        assert int(err.abs().sum().item()) == 0
-        frontier = children
-    return out
+    return perft(R, start_record(name, castling=castling), depth, chunk=50000)
 
 
 @pytest.mark.parametrize("name", list(PERFT))
@@ -346,6 +324,18 @@ def test_async_dense_pipeline_matches_sync():
     recs = before[:256].cpu().numpy()
     assert np.array_equal(a.planes_buffer()[:256].cpu().numpy(), o.encode(recs, recs[:, g.off_turn].astype(np.int32)))
     assert np.array_equal(a.mask_buffer()[:256].cpu().numpy(), o.mask(recs))
+
+
+def test_dlpack_handoff_is_zero_copy():
+    R, n = 8, 64
+    env = BatchedEnv(R, n)
+    env.load(start_record("EIGHT_SIMPLE"))
+    env.observe(planes=True, mask=True)
+    for name, buf in (("planes", env.planes_buffer()), ("mask", env.mask_buffer()), ("boards", env.boards)):
+        t = torch.from_dlpack(env.dlpack(name))
+        assert t.data_ptr() == buf.data_ptr() and t.shape == buf.shape and t.device == buf.device
+    torch.cuda.synchronize()
+    assert torch.equal(torch.from_dlpack(env.dlpack("planes")), env.planes_buffer())
 
 
 def test_full_size_properties():
