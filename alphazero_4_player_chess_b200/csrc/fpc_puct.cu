@@ -62,28 +62,34 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) tree_descend_kernel(const fpc_
   const int32_t *visits = T.visits + slab, *first_child = T.first_child + slab, *n_children = T.n_children + slab;
   const double *value_sum = T.value_sum + slab;
   const float *prior = T.prior + slab;
-  int node = 0, nc;
-  while ((nc = n_children[node]) > 0) {
-    const int fc = first_child[node];
-    const double lg = log(sqrt((double)visits[node]));
+  // One dependent memory round per level: while scanning the children of `node` every lane also fetches
+  // its child's own child range, and the winner's (first_child, n_children, visits) travel with the arg-max.
+  int node = 0;
+  int nc = n_children[0], fc = first_child[0], nv = visits[0];
+  while (nc > 0) {
+    const double lg = log(sqrt((double)nv));
     double best = -CUDART_INF;
-    int best_i = 0x7fffffff;
+    int best_i = 0x7fffffff, b_nc = 0, b_fc = 0, b_nv = 0;
     for (int i = lane; i < nc; i += 32) {
       const int n = visits[fc + i];
+      const int c_nc = n_children[fc + i], c_fc = first_child[fc + i];
       const double q = n > 0 ? value_sum[fc + i] / (double)n : 0.0;
       const double ucb = q + T.C * sqrt(lg / (double)(1 + n)) * (double)prior[fc + i];
       if (ucb > best) {  // strict: the first maximum wins
         best = ucb;
         best_i = i;
+        b_nc = c_nc, b_fc = c_fc, b_nv = n;
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double ob = __shfl_xor_sync(FULL, best, o);
       const int oi = __shfl_xor_sync(FULL, best_i, o);
+      const int o_nc = __shfl_xor_sync(FULL, b_nc, o), o_fc = __shfl_xor_sync(FULL, b_fc, o), o_nv = __shfl_xor_sync(FULL, b_nv, o);
       if (oi != 0x7fffffff && (best_i == 0x7fffffff || ob > best || (ob == best && oi < best_i))) {
         best = ob;
         best_i = oi;
+        b_nc = o_nc, b_fc = o_fc, b_nv = o_nv;
       }
     }
     if (best_i == 0x7fffffff) {  // "Failed to select a child." (node.cpp:72-75)
@@ -95,6 +101,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) tree_descend_kernel(const fpc_
       return;
     }
     node = fc + best_i;
+    nc = b_nc, fc = b_fc, nv = b_nv;
   }
   // materialise the leaf's board: parent's board + MakeMove(Move(flat_index)) (node.cpp:87-92)
   uint8_t *pool = T.boards + (size_t)g * T.board_cap * G::REC;
@@ -183,15 +190,26 @@ __global__ void __launch_bounds__(EXP_THREADS) tree_expand_backup_kernel(const f
     value = values[g];
     // ---- softmax over the whole action space (mcts.py:67), online max / sum -----------------
     const float *lg = logits + (size_t)g * G::ASZ;
+    // two passes (the second one hits L2): loads are independent of the running max / sum, so many are in flight
     float m = -CUDART_INF_F, s = 0.0f;
+    const float4 *lg4 = reinterpret_cast<const float4 *>(lg);
+#pragma unroll 8
     for (int i = tid; i < G::ASZ / 4; i += EXP_THREADS) {
-      const float4 v = __ldg(reinterpret_cast<const float4 *>(lg) + i);
-      const float vm = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-      if (vm > m) {
-        s *= expf(m - vm);
-        m = vm;
-      }
-      s += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+      const float4 v = __ldg(lg4 + i);
+      m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    if (lane == 0) red_m[warp] = m;
+    __syncthreads();
+    m = red_m[0];
+#pragma unroll
+    for (int w = 1; w < EXP_THREADS / 32; ++w) m = fmaxf(m, red_m[w]);
+    __syncthreads();
+#pragma unroll 8
+    for (int i = tid; i < G::ASZ / 4; i += EXP_THREADS) {
+      const float4 v = __ldg(lg4 + i);
+      s += (expf(v.x - m) + expf(v.y - m)) + (expf(v.z - m) + expf(v.w - m));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
