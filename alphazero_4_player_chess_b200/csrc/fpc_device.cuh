@@ -67,7 +67,7 @@ struct alignas(16) WarpScratch {
   uint32_t mask_bits[G::MASK_STRIDE];    // legal-move mask, 1 bit per action
   uint32_t plane_bits[G::PLANE_STRIDE];  // input planes, 1 bit per cell
   uint32_t moves[MAX_MOVES + 4];  // compact moves: key<<14 | castle<<8 | to_mb, key = flat*8 + promo
-  uint8_t mb[256];                // mailbox board
+  uint8_t mb[1024];               // mailbox board in four layouts (see put_cell): rows, columns, diagonals, anti-diagonals
   uint8_t rec[256];               // raw record staging (in and out)
   uint8_t plist[64];              // mailbox squares of the mover's pieces
   uint8_t rights[4];
@@ -94,51 +94,145 @@ __device__ __forceinline__ uint32_t cell(const uint8_t *mb, int i, const Patch &
   return v;
 }
 
+// ---- the mailbox in four layouts -------------------------------------------------------------------
+// Cell (R1, C1) of the 16x16 mailbox (R1 = row+1, C1 = col+1) is stored four times, so that every line
+// through a square is 16 contiguous, 16-byte aligned bytes -- ONE shared-memory load per line:
+//   rows   mb[        R1 << 4            | C1]   E/W  rays, position C1
+//   cols   mb[ 256 | (C1 << 4)           | R1]   S/N  rays, position R1
+//   dias   mb[ 512 | ((R1 - C1) & 15) << 4 | C1]   SE/NW rays, position C1 (C1+1 => R1+1)
+//   antis  mb[ 768 | ((R1 + C1) & 15) << 4 | C1]   NE/SW rays, position C1 (C1+1 => R1-1)
+// A diagonal id wraps round the 16x16 torus, but every wrap crosses the WALL border, so a scan from an
+// on-board square never reaches the other part.  Ray walks become bit scans over a line vector: the
+// dependent chain of byte loads (one per step) is gone, which matters twice over when the streaming
+// expand_kernel keeps the load/store pipe busy (tools/contention.cu).
+__host__ __device__ __forceinline__ int idx_col(int m) { return 256 | ((m & 15) << 4) | (m >> 4); }
+__host__ __device__ __forceinline__ int idx_dia(int m) { return 512 | ((((m >> 4) - (m & 15)) & 15) << 4) | (m & 15); }
+__host__ __device__ __forceinline__ int idx_ant(int m) { return 768 | ((((m >> 4) + (m & 15)) & 15) << 4) | (m & 15); }
+
+__host__ __device__ __forceinline__ void put_cell(uint8_t *mb, int m, uint32_t v) {
+  mb[m] = (uint8_t)v;
+  mb[idx_col(m)] = (uint8_t)v;
+  mb[idx_dia(m)] = (uint8_t)v;
+  mb[idx_ant(m)] = (uint8_t)v;
+}
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ int fpc_ffs(uint32_t x) { return __ffs((int)x); }
+__device__ __forceinline__ int fpc_clz(uint32_t x) { return __clz((int)x); }
+#else
+inline int fpc_ffs(uint32_t x) { return __builtin_ffs((int)x); }
+inline int fpc_clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+#endif
+
+struct Line {
+  uint32_t w[4];
+};
+__device__ __forceinline__ Line load_line(const uint8_t *base16) {
+  const uint4 v = *reinterpret_cast<const uint4 *>(base16);
+  Line l;
+  l.w[0] = v.x, l.w[1] = v.y, l.w[2] = v.z, l.w[3] = v.w;
+  return l;
+}
+__device__ __forceinline__ uint32_t line_byte(const Line &l, int pos) {
+  const uint32_t w = pos < 8 ? (pos < 4 ? l.w[0] : l.w[1]) : (pos < 12 ? l.w[2] : l.w[3]);
+  return (w >> ((pos & 3) * 8)) & 0xffu;
+}
+__device__ __forceinline__ void line_set(Line &l, int pos, uint32_t val) {
+  const uint32_t sh = (pos & 3) * 8, keep = ~(0xffu << sh), ins = val << sh;
+  const int wi = pos >> 2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (wi == i) l.w[i] = (l.w[i] & keep) | ins;
+}
+// bit i set <=> byte i is not EMPTY.  EMPTY = 0x18; a piece has bit 7, WALL (0x1C) has bit 2.
+__device__ __forceinline__ uint32_t line_occupancy(const Line &l) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t t = (l.w[i] | (l.w[i] << 5)) & 0x80808080u;
+    m |= ((((t >> 7) * 0x00204081u) >> 21) & 15u) << (4 * i);
+  }
+  return m;
+}
+// Nearest non-empty cells on either side of position k (1 <= k <= 14; the WALL border guarantees both).
+struct Nearest {
+  uint32_t lo, hi;    // piece bytes (WALL for the border)
+  bool lo_adj, hi_adj;  // at distance 1
+};
+__device__ __forceinline__ Nearest line_nearest(const Line &l, int k) {
+  const uint32_t occ = line_occupancy(l);
+  const int ph = fpc_ffs(occ & (0xfffeu << k)) - 1;
+  const int pl = 31 - fpc_clz(occ & ((1u << k) - 1u));
+  Nearest n;
+  n.hi = line_byte(l, ph);
+  n.lo = line_byte(l, pl);
+  n.hi_adj = ph == k + 1;
+  n.lo_adj = pl == k - 1;
+  return n;
+}
+// Apply one patched cell (mailbox index q -> val) to the four lines through (R1, C1).
+__device__ __forceinline__ void patch_lines(Line &row, Line &col, Line &dia, Line &ant, int R1, int C1, int q, uint32_t val) {
+  const int qR = q >> 4, qC = q & 15;
+  if (qR == R1) line_set(row, qC, val);
+  if (qC == C1) line_set(col, qR, val);
+  if (((qR - qC) & 15) == ((R1 - C1) & 15)) line_set(dia, qC, val);
+  if (((qR + qC) & 15) == ((R1 + C1) & 15)) line_set(ant, qC, val);
+}
+
 // chess::Board::GetAttackers2 with limit 1 == IsAttackedByTeam (engine/board.cpp:606-787).
 // `s` must be an on-board mailbox square.  Rook rays in the reference run to the edge of the
 // R x R box (:632) and bishop rays to the first illegal square (:658); with WALL in the (always
-// empty) cut corners both stop at the same attackers.
+// empty) cut corners both stop at the same attackers.  Sliders (:612-674), pawns (:697-750) and kings
+// (:753-772) come out of the four line vectors; knights (:676-694, all eight squares whatever IA is)
+// are eight independent byte loads.
 template <class G, bool PATCHED>
 __device__ bool attacked_by_team(const uint8_t *mb, int team, int s, const Patch &p) {
-#pragma unroll
-  for (int dir = 0; dir < 8; ++dir) {
-    const int d = qdelta(dir);
-    int i = s + d;
-    uint32_t v;
-    while ((v = cell<PATCHED>(mb, i, p)) == EMPTY) i += d;
-    if (present(v) && team_of(v) == team) {
-      int t = type_of(v);
-      if (t == QUEEN || t == ((dir & 1) ? BISHOP : ROOK)) return true;
-    }
-  }
-  const int r = (s >> 4) - 1, c = (s & 15) - 1;
-  // knights: all eight squares whatever IA is (:676-694)
+  const int R1 = s >> 4, C1 = s & 15;
+  Line row = load_line(mb + (R1 << 4));
+  Line col = load_line(mb + 256 + (C1 << 4));
+  Line dia = load_line(mb + 512 + (((R1 - C1) & 15) << 4));
+  Line ant = load_line(mb + 768 + (((R1 + C1) & 15) << 4));
+  uint32_t kn[8];
+  const int r = R1 - 1, c = C1 - 1;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    int tr = r + kdrow(k), tc = c + kdcol(k);
-    if ((unsigned)tr < (unsigned)G::R && (unsigned)tc < (unsigned)G::R) {
-      uint32_t v = cell<PATCHED>(mb, G::mb(tr, tc), p);
-      if (present(v) && team_of(v) == team && type_of(v) == KNIGHT) return true;
-    }
+    const int tr = r + kdrow(k), tc = c + kdcol(k);
+    kn[k] = ((unsigned)tr < (unsigned)G::R && (unsigned)tc < (unsigned)G::R) ? cell<PATCHED>(mb, G::mb(tr, tc), p) : WALL;
   }
-  // pawns (:697-750): RED attacks from the row below, YELLOW from the row above,
-  // BLUE from the column to the left, GREEN from the column to the right.
+  if (PATCHED) {
+    if (p.a < 256) patch_lines(row, col, dia, ant, R1, C1, p.a, EMPTY);
+    if (p.c < 256) patch_lines(row, col, dia, ant, R1, C1, p.c, EMPTY);
+    if (p.b < 256) patch_lines(row, col, dia, ant, R1, C1, p.b, p.bp);
+    if (p.d < 256) patch_lines(row, col, dia, ant, R1, C1, p.d, p.dp);
+  }
+  const Nearest nr = line_nearest(row, C1), nc = line_nearest(col, R1), nd = line_nearest(dia, C1), na = line_nearest(ant, C1);
+  bool hit = false;
+  auto slider = [&](uint32_t v, int straight) {
+    const int t = type_of(v);
+    hit |= present(v) && team_of(v) == team && (t == QUEEN || t == (straight ? ROOK : BISHOP));
+  };
+  slider(nr.lo, 1), slider(nr.hi, 1), slider(nc.lo, 1), slider(nc.hi, 1);
+  slider(nd.lo, 0), slider(nd.hi, 0), slider(na.lo, 0), slider(na.hi, 0);
+  const uint32_t knight = mk_piece(team, KNIGHT) & 0xbfu, king = mk_piece(team, KING) & 0xbfu;  // colour bit 6 ignored: team = bit 5
+#pragma unroll
+  for (int k = 0; k < 8; ++k) hit |= (kn[k] & 0xbfu) == knight;
+  // adjacent kings: the nearest non-empty cell at distance 1 on each of the eight rays
+  auto adj_king = [&](uint32_t v, bool adj) { hit |= adj && (v & 0xbfu) == king; };
+  adj_king(nr.lo, nr.lo_adj), adj_king(nr.hi, nr.hi_adj), adj_king(nc.lo, nc.lo_adj), adj_king(nc.hi, nc.hi_adj);
+  adj_king(nd.lo, nd.lo_adj), adj_king(nd.hi, nd.hi_adj), adj_king(na.lo, na.lo_adj), adj_king(na.hi, na.hi_adj);
+  // pawns: RED attacks from the row below, YELLOW from the row above, BLUE from the column to the
+  // left, GREEN from the column to the right.  Diagonal neighbours: dia.lo = (R1-1,C1-1), dia.hi =
+  // (R1+1,C1+1), ant.lo = (R1+1,C1-1), ant.hi = (R1-1,C1+1).
+  const uint32_t d_lo = nd.lo_adj ? nd.lo : EMPTY, d_hi = nd.hi_adj ? nd.hi : EMPTY;
+  const uint32_t a_lo = na.lo_adj ? na.lo : EMPTY, a_hi = na.hi_adj ? na.hi : EMPTY;
   if (team == 0) {
     const uint32_t red = mk_piece(0, PAWN), yellow = mk_piece(2, PAWN);
-    if (cell<PATCHED>(mb, s + 15, p) == red || cell<PATCHED>(mb, s + 17, p) == red) return true;
-    if (cell<PATCHED>(mb, s - 17, p) == yellow || cell<PATCHED>(mb, s - 15, p) == yellow) return true;
+    hit |= a_lo == red || d_hi == red || d_lo == yellow || a_hi == yellow;
   } else {
     const uint32_t blue = mk_piece(1, PAWN), green = mk_piece(3, PAWN);
-    if (cell<PATCHED>(mb, s - 17, p) == blue || cell<PATCHED>(mb, s + 15, p) == blue) return true;
-    if (cell<PATCHED>(mb, s - 15, p) == green || cell<PATCHED>(mb, s + 17, p) == green) return true;
+    hit |= d_lo == blue || a_lo == blue || a_hi == green || d_hi == green;
   }
-  // kings (:753-772)
-#pragma unroll
-  for (int dir = 0; dir < 8; ++dir) {
-    uint32_t v = cell<PATCHED>(mb, s + qdelta(dir), p);
-    if (present(v) && team_of(v) == team && type_of(v) == KING) return true;
-  }
-  return false;
+  return hit;
 }
 
 // engine/board.cpp:23-30 + :1474-1524 GetRookLocationType: 0 kingside, 1 queenside, -1 neither.
@@ -375,15 +469,15 @@ __device__ __forceinline__ void make_compact(WarpScratch<G> &s, uint32_t mv) {
     else if (ct == 1 && ((cur >> 5) & 1)) s.rights[turn] = 0x80 | (cur & 0x40);
   }
   if (present(cap) && type_of(cap) == KING) s.king[color_of(cap)] = NO_SQ;
-  s.mb[from] = EMPTY;
-  s.mb[to] = promo != NO_PIECE ? mk_piece(turn, promo) : piece;
+  put_cell(s.mb, from, EMPTY);
+  put_cell(s.mb, to, promo != NO_PIECE ? mk_piece(turn, promo) : piece);
   if (type == KING) s.king[turn] = to;
   if (castle) {
     int rf, rt;
     castle_rook(from, to, castle, rf, rt);
     const uint32_t rook = s.mb[rf];
-    s.mb[rf] = EMPTY;
-    s.mb[rt] = rook;
+    put_cell(s.mb, rf, EMPTY);
+    put_cell(s.mb, rt, rook);
   }
   s.turn = (turn + 1) & 3;
 }

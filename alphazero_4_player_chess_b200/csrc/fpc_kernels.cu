@@ -78,7 +78,8 @@ struct HalfRow {
 template <class G>
 __device__ __forceinline__ void load_record(WarpScratch<G> &s, const uint8_t *rec_g, int lane) {
   // mailbox <- WALL; record -> staging (coalesced 16-byte loads: the record is contiguous)
-  reinterpret_cast<uint2 *>(s.mb)[lane] = make_uint2(0x1C1C1C1Cu, 0x1C1C1C1Cu);
+  reinterpret_cast<uint4 *>(s.mb)[lane] = make_uint4(0x1C1C1C1Cu, 0x1C1C1C1Cu, 0x1C1C1C1Cu, 0x1C1C1C1Cu);
+  reinterpret_cast<uint4 *>(s.mb)[lane + 32] = make_uint4(0x1C1C1C1Cu, 0x1C1C1C1Cu, 0x1C1C1C1Cu, 0x1C1C1C1Cu);
   if (lane < G::REC / 16)
     reinterpret_cast<uint4 *>(s.rec)[lane] = reinterpret_cast<const uint4 *>(rec_g)[lane];  // may be updated in place: no __ldg
   if (lane < 4) s.king[lane] = NO_SQ;
@@ -116,7 +117,7 @@ __device__ __forceinline__ void store_record(WarpScratch<G> &s, uint8_t *rec_g, 
 // and (playout) the move choice and make-move.  It touches only the board store and compact
 // per-game outputs.
 template <class G>
-__global__ void __launch_bounds__(BLOCK_THREADS, 12) rules_kernel(const __grid_constant__ ObserveParams P) {
+__global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_constant__ ObserveParams P) {
   __shared__ WarpScratch<G> scratch[WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * WARPS_PER_BLOCK + wib;
@@ -151,7 +152,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 12) rules_kernel(const __grid_c
       uint32_t p = EMPTY;
       if (hr.on_board(j)) {
         p = s.rec[r * G::R + c];
-        s.mb[G::mb(r, c)] = (uint8_t)p;
+        if (!present(p)) p = EMPTY;  // one canonical empty byte: the line scans test bits 7 and 2
+        put_cell(s.mb, G::mb(r, c), p);
         if (present(p) && type_of(p) == KING) s.king[color_of(p)] = (uint8_t)G::mb(r, c);
       }
       const bool mine = present(p) && color_of(p) == turn;

@@ -13,14 +13,14 @@ using namespace fpc;
 
 template <class G>
 static void load(WarpScratch<G> &s, const uint8_t *rec) {
-  memset(s.mb, WALL, 256);
+  memset(s.mb, WALL, sizeof s.mb);
   for (int i = 0; i < 4; ++i) s.king[i] = NO_SQ, s.rights[i] = rec[G::OFF_RIGHTS + i];
   s.turn = rec[G::OFF_TURN] & 3;
   for (int sq = 0; sq < G::NSQ; ++sq) {
     int r = sq / G::R, c = sq % G::R;
     if (!G::legal(r, c)) continue;
     uint32_t p = rec[sq];
-    s.mb[G::mb(r, c)] = (uint8_t)p;
+    put_cell(s.mb, G::mb(r, c), present(p) ? p : EMPTY);
     if (present(p) && type_of(p) == KING) s.king[color_of(p)] = (uint8_t)G::mb(r, c);
   }
 }
