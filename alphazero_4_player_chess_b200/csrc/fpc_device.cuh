@@ -276,100 +276,105 @@ __device__ __forceinline__ void castle_rook(int from_mb, int to_mb, int castle, 
   rook_from = from_mb + u * (castle == 2 ? 3 : 4);  // castle: 1 queenside, 2 kingside
 }
 
-// Work item -> moves.  Item (piece, dir) of the mover's piece at `from`.  Returns the number of
-// pseudo-legal moves of the item and, through the out params, how to enumerate them:
-//   kind 0: to = from + delta*(j+1), plane = plane0 + j      (rays, steps, jumps, pushes)
-//   kind 1: to = from + delta, plane0, promotion N,B,R,Q for j = 0..3 (engine/board.cpp:82-88)
+// Work item -> moves.  Item (piece, line) of the mover's piece at `from`; a line is one of the four
+// lines through the square (0 row: W/E, 1 column: N/S, 2 diagonal: NW/SE, 3 anti-diagonal: SW/NE) and
+// yields up to two RUNS of moves, one per direction:
+//   kind 0: to = from + delta*(j+1), plane = plane0 + j, j < cnt   (rays, steps, jumps, pushes)
+//   kind 1: run 0 only: to = from + delta, plane0, promotion N,B,R,Q for j = 0..3 (engine/board.cpp:82-88)
+// Sliders and the king read their line as one 16-byte vector (no per-step loads); a knight item is two of
+// the eight jumps; a pawn item is one of push / double push / the two captures.
+struct Run {
+  int delta, plane0, cnt;
+};
+// plane-order direction index (move.cpp:13-14) of the "lo" side of a line; the "hi" side is +4
+__device__ __forceinline__ int line_lo_dir(int line) { return (0x3102 >> (line * 4)) & 15; }  // W(2) N(0) NW(1) SW(3)
+
 template <class G>
-__device__ int gen_item(const uint8_t *mb, int from, int dir, int &delta, int &plane0, int &kind) {
+__device__ void gen_item(const uint8_t *mb, int from, int line, Run &lo, Run &hi, int &kind) {
   constexpr int R = G::R;
   const uint32_t p = mb[from];
   const int type = type_of(p), color = color_of(p), team = team_of(p);
-  const int r = (from >> 4) - 1, c = (from & 15) - 1;
+  const int R1 = from >> 4, C1 = from & 15;
+  const int r = R1 - 1, c = C1 - 1;
   kind = 0;
-  delta = 0;
-  plane0 = 0;
-  switch (type) {
-    case PAWN: {  // engine/board.cpp:97-177 GetPawnMoves2
-      if (dir > 3) return 0;
-      // forward direction as a plane direction: RED N(0) BLUE E(6) YELLOW S(4) GREEN W(2)
-      const int fdir = color == 0 ? 0 : (color == 1 ? 6 : (color == 2 ? 4 : 2));
-      const int fwd = qdelta(fdir);
-      int to, pdir, dist = 1;
-      if (dir == 0) {
-        to = from + fwd;
-        if (mb[to] != EMPTY) return 0;
-        pdir = fdir;
-      } else if (dir == 1) {
-        const bool not_moved = color == 0 ? r == R - 2 : (color == 1 ? c == 1 : (color == 2 ? r == 1 : c == R - 2));
-        if (!not_moved || mb[from + fwd] != EMPTY) return 0;
-        to = from + 2 * fwd;
-        if (mb[to] != EMPTY) return 0;
-        pdir = fdir;
-        dist = 2;
-      } else {
-        // captures on the two forward diagonals, against the other team only (:153-176)
-        // RED: NW(1),NE(7)  YELLOW: SW(3),SE(5)  BLUE: NE(7),SE(5)  GREEN: NW(1),SW(3)
-        const int first = dir == 2;
-        pdir = color == 0 ? (first ? 1 : 7) : (color == 2 ? (first ? 3 : 5) : (color == 1 ? (first ? 7 : 5) : (first ? 1 : 3)));
-        to = from + qdelta(pdir);
-        const uint32_t o = mb[to];
-        if (!present(o) || team_of(o) == team) return 0;
-      }
-      delta = to - from;
-      plane0 = pdir * (R - 1) + dist - 1;
-      // promotion line (:58-76): RED row R/4, YELLOW row 3R/4, BLUE col 3R/4, GREEN col R/4
-      const int tr = (to >> 4) - 1, tc = (to & 15) - 1;
-      const bool promo = color == 0 ? tr == R / 4 : (color == 2 ? tr == 3 * R / 4 : (color == 1 ? tc == 3 * R / 4 : tc == R / 4));
-      if (promo) {
-        kind = 1;
-        return 4;
-      }
-      return 1;
+  lo.delta = lo.plane0 = lo.cnt = 0;
+  hi.delta = hi.plane0 = hi.cnt = 0;
+  if (type == PAWN) {  // engine/board.cpp:97-177 GetPawnMoves2; `line` = 0 push, 1 double push, 2 / 3 captures
+    // forward direction as a plane direction: RED N(0) BLUE E(6) YELLOW S(4) GREEN W(2)
+    const int fdir = color == 0 ? 0 : (color == 1 ? 6 : (color == 2 ? 4 : 2));
+    const int fwd = qdelta(fdir);
+    int to, pdir, dist = 1;
+    if (line == 0) {
+      to = from + fwd;
+      if (mb[to] != EMPTY) return;
+      pdir = fdir;
+    } else if (line == 1) {
+      const bool not_moved = color == 0 ? r == R - 2 : (color == 1 ? c == 1 : (color == 2 ? r == 1 : c == R - 2));
+      if (!not_moved || mb[from + fwd] != EMPTY) return;
+      to = from + 2 * fwd;
+      if (mb[to] != EMPTY) return;
+      pdir = fdir;
+      dist = 2;
+    } else {
+      // captures on the two forward diagonals, against the other team only (:153-176)
+      // RED: NW(1),NE(7)  YELLOW: SW(3),SE(5)  BLUE: NE(7),SE(5)  GREEN: NW(1),SW(3)
+      const int first = line == 2;
+      pdir = color == 0 ? (first ? 1 : 7) : (color == 2 ? (first ? 3 : 5) : (color == 1 ? (first ? 7 : 5) : (first ? 1 : 3)));
+      to = from + qdelta(pdir);
+      const uint32_t o = mb[to];
+      if (!present(o) || team_of(o) == team) return;
     }
-    case KNIGHT: {  // engine/board.cpp:179-207: |drow| runs 1..IA-1 only
-      const int dr = kdrow(dir), dc = kdcol(dir);
-      if ((dr < 0 ? -dr : dr) >= G::IA) return 0;
+    lo.delta = to - from;
+    lo.plane0 = pdir * (R - 1) + dist - 1;
+    // promotion line (:58-76): RED row R/4, YELLOW row 3R/4, BLUE col 3R/4, GREEN col R/4
+    const int tr = (to >> 4) - 1, tc = (to & 15) - 1;
+    const bool promo = color == 0 ? tr == R / 4 : (color == 2 ? tr == 3 * R / 4 : (color == 1 ? tc == 3 * R / 4 : tc == R / 4));
+    kind = promo ? 1 : 0;
+    lo.cnt = promo ? 4 : 1;
+    return;
+  }
+  if (type == KNIGHT) {  // engine/board.cpp:179-207: |drow| runs 1..IA-1 only; jumps 2*line and 2*line+1
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = 2 * line + h;
+      const int dr = kdrow(k), dc = kdcol(k);
+      Run &out = h ? hi : lo;
+      if ((dr < 0 ? -dr : dr) >= G::IA) continue;
       const int tr = r + dr, tc = c + dc;
-      if ((unsigned)tr >= (unsigned)R || (unsigned)tc >= (unsigned)R) return 0;
+      if ((unsigned)tr >= (unsigned)R || (unsigned)tc >= (unsigned)R) continue;
       const int to = G::mb(tr, tc);
       const uint32_t o = mb[to];
-      if (o == WALL || (present(o) && team_of(o) == team)) return 0;
-      delta = to - from;
-      plane0 = 8 * (R - 1) + dir;
-      return 1;
+      if (o == WALL || (present(o) && team_of(o) == team)) continue;
+      out.delta = to - from;
+      out.plane0 = 8 * (R - 1) + k;
+      out.cnt = 1;
     }
-    case KING: {  // engine/board.cpp:322-341 (castling is a separate item)
-      const int d = qdelta(dir);
-      const uint32_t o = mb[from + d];
-      if (o == WALL || (present(o) && team_of(o) == team)) return 0;
-      delta = d;
-      plane0 = dir * (R - 1);
-      return 1;
-    }
-    case BISHOP:
-      if (!(dir & 1)) return 0;
-      break;
-    case ROOK:
-      if (dir & 1) return 0;
-      break;
-    case QUEEN:
-      break;
-    default:
-      return 0;
+    return;
   }
-  // sliders: engine/board.cpp:209-238 AddMovesFromIncrMovement2
-  const int d = qdelta(dir);
-  int i = from + d, cnt = 0;
-  uint32_t o;
-  while ((o = mb[i]) == EMPTY) {
-    ++cnt;
-    i += d;
+  const bool straight = line < 2;
+  if (type == BISHOP ? straight : (type == ROOK ? !straight : (type != QUEEN && type != KING))) return;
+  // the line through `from`: sliders (engine/board.cpp:209-238 AddMovesFromIncrMovement2) and king steps (:322-341)
+  const int k = line == 1 ? R1 : C1;
+  const Line l = load_line(line == 0 ? mb + (R1 << 4)
+                                     : (line == 1 ? mb + 256 + (C1 << 4)
+                                                  : (line == 2 ? mb + 512 + (((R1 - C1) & 15) << 4) : mb + 768 + (((R1 + C1) & 15) << 4))));
+  const int dlo = line_lo_dir(line), dhi = dlo + 4;
+  lo.delta = qdelta(dlo);
+  lo.plane0 = dlo * (R - 1);
+  hi.delta = qdelta(dhi);
+  hi.plane0 = dhi * (R - 1);
+  if (type == KING) {
+    const uint32_t a = line_byte(l, k - 1), b = line_byte(l, k + 1);
+    lo.cnt = !(a == WALL || (present(a) && team_of(a) == team));
+    hi.cnt = !(b == WALL || (present(b) && team_of(b) == team));
+    return;
   }
-  if (present(o) && team_of(o) != team) ++cnt;
-  delta = d;
-  plane0 = dir * (R - 1);
-  return cnt;
+  const uint32_t occ = line_occupancy(l);
+  const int ph = fpc_ffs(occ & (0xfffeu << k)) - 1;
+  const int pl = 31 - fpc_clz(occ & ((1u << k) - 1u));
+  const uint32_t bh = line_byte(l, ph), bl = line_byte(l, pl);
+  hi.cnt = ph - k - 1 + (present(bh) && team_of(bh) != team);
+  lo.cnt = k - pl - 1 + (present(bl) && team_of(bl) != team);
 }
 
 // Castling candidate (engine/board.cpp:343-465).  side: 0 queenside, 1 kingside.  Returns the

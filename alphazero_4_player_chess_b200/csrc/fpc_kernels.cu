@@ -186,14 +186,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_c
     int n_pseudo = 0;
     bool overflow = false;
     if (king_sq != NO_SQ) {
-      const int items = np * 8;
+      const int items = np * 4;  // (piece, line): two runs of moves each
       for (int base = 0; base < items; base += 32) {
         const int item = base + lane;
-        int cnt = 0, delta = 0, plane0 = 0, kind = 0, from = 0;
+        Run lo{0, 0, 0}, hi{0, 0, 0};
+        int kind = 0, from = 0;
         if (item < items) {
-          from = s.plist[item >> 3];
-          cnt = gen_item<G>(s.mb, from, item & 7, delta, plane0, kind);
+          from = s.plist[item >> 2];
+          gen_item<G>(s.mb, from, item & 3, lo, hi, kind);
         }
+        const int cnt = lo.cnt + hi.cnt;
         // exclusive prefix sum of cnt over the warp
         int incl = cnt;
 #pragma unroll
@@ -206,12 +208,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_c
         if (n_pseudo + total > MAX_MOVES) {
           overflow = true;
         } else {
-          for (int j = 0; j < cnt; ++j) {
-            uint32_t mv;
-            if (kind == 0) mv = pack_compact<G>(from, from + delta * (j + 1), plane0 + j, NO_PIECE, 0);
-            else mv = pack_compact<G>(from, from + delta, plane0, KNIGHT + j, 0);
-            s.moves[at + j] = mv;
-          }
+          for (int j = 0; j < lo.cnt; ++j)
+            s.moves[at++] = kind == 0 ? pack_compact<G>(from, from + lo.delta * (j + 1), lo.plane0 + j, NO_PIECE, 0)
+                                      : pack_compact<G>(from, from + lo.delta, lo.plane0, KNIGHT + j, 0);
+          for (int j = 0; j < hi.cnt; ++j) s.moves[at++] = pack_compact<G>(from, from + hi.delta * (j + 1), hi.plane0 + j, NO_PIECE, 0);
           n_pseudo += total;
         }
       }
@@ -274,6 +274,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_c
       pick = (uint32_t)(((mix64(P.seed, game_id, (uint64_t)ply) >> 32) * (uint64_t)n_legal) >> 32);
     const bool want_lists = P.moves || P.flat;
     if (want_lists || P.mask_bits || P.playout) {
+      // pad to a multiple of four with keys above every real one: the rank loop compares four keys per load
+      if (lane < 4) s.moves[n_legal + lane] = 0xffffffffu;
+      __syncwarp();
       for (int base = 0; base < n_legal; base += 32) {
         const int i = base + lane;
         if (i < n_legal) {
@@ -282,7 +285,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_c
           if (P.mask_bits) atomicOr(&s.mask_bits[flat >> 5], 1u << (flat & 31));
           if (want_lists || P.playout) {
             int rank = 0;
-            for (int j = 0; j < n_legal; ++j) rank += s.moves[j] < mv;
+            for (int j = 0; j < n_legal; j += 4) {
+              const uint4 q = *reinterpret_cast<const uint4 *>(&s.moves[j]);
+              rank += (q.x < mv) + (q.y < mv) + (q.z < mv) + (q.w < mv);
+            }
             if (P.moves) P.moves[(size_t)g * MAX_MOVES + rank] = expand_move<G>(s.mb, s.rights, mv);
             if (P.flat) P.flat[(size_t)g * MAX_MOVES + rank] = (int32_t)flat;
             if ((uint32_t)rank == pick) chosen_mv = mv;

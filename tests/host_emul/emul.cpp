@@ -51,12 +51,14 @@ static int legal_compact(WarpScratch<G> &s, std::vector<uint32_t> &out, int *sta
       int from = G::mb(r, c);
       uint32_t p = s.mb[from];
       if (!present(p) || color_of(p) != turn) continue;
-      for (int dir = 0; dir < 8; ++dir) {
-        int delta, plane0, kind;
-        int cnt = gen_item<G>(s.mb, from, dir, delta, plane0, kind);
-        for (int j = 0; j < cnt; ++j)
-          pseudo.push_back(kind == 0 ? pack_compact<G>(from, from + delta * (j + 1), plane0 + j, NO_PIECE, 0)
-                                     : pack_compact<G>(from, from + delta, plane0, KNIGHT + j, 0));
+      for (int line = 0; line < 4; ++line) {
+        Run lo, hi;
+        int kind;
+        gen_item<G>(s.mb, from, line, lo, hi, kind);
+        for (int j = 0; j < lo.cnt; ++j)
+          pseudo.push_back(kind == 0 ? pack_compact<G>(from, from + lo.delta * (j + 1), lo.plane0 + j, NO_PIECE, 0)
+                                     : pack_compact<G>(from, from + lo.delta, lo.plane0, KNIGHT + j, 0));
+        for (int j = 0; j < hi.cnt; ++j) pseudo.push_back(pack_compact<G>(from, from + hi.delta * (j + 1), hi.plane0 + j, NO_PIECE, 0));
       }
     }
     for (int side = 0; side < 2; ++side) {
