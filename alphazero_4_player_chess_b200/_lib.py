@@ -33,7 +33,7 @@ SIGNATURES = {
     "fpc_observe": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "fpc_join": (_i, [_vp]),
     "fpc_profile_enable": (_i, [_i]),
-    "fpc_profile_read": (_i, [_vp, _vp]),
+    "fpc_profile_read": (_i, [_vp, _vp, _vp]),
     "fpc_encode": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "fpc_make_moves": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp]),
     "fpc_make_index": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp]),

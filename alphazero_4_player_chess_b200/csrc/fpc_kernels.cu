@@ -496,7 +496,8 @@ struct SideState {
   // optional CUDA-event timing of expand_kernel on its own stream (fpc_profile_enable / _read)
   bool prof_on = false;
   int prof_n = 0;
-  std::vector<cudaEvent_t> prof_ev;
+  std::vector<cudaEvent_t> prof_ev;   // expand_kernel: start/stop pairs
+  std::vector<cudaEvent_t> prof_ev_r; // rules_kernel (dense path): start/stop pairs
 };
 constexpr int PROF_MAX = 4096;
 static thread_local SideState g_side[16];
@@ -572,8 +573,25 @@ static int launch_observe(ObserveParams p, DenseOut d, cudaStream_t st, F after_
   CK(cudaEventRecord(S->fork, st));
   CK(cudaStreamWaitEvent(S->hi, S->fork, 0));
   if (S->expand_recorded[b]) CK(cudaStreamWaitEvent(S->hi, S->expand_done[b], 0));
+  // Both kernels ask for the same shared-memory carveout: CTAs of rules_kernel (24 KB of shared memory each) and of
+  // expand_kernel (none) share SMs, and an SM only changes its L1 / shared split when it is empty.
+  {
+    static thread_local bool carveout_set[16] = {false};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    const char *env = getenv("FPC_CARVEOUT");
+    const int pct = env ? atoi(env) : 100;
+    if (dev >= 0 && dev < 16 && !carveout_set[dev] && pct >= 0) {
+      CK(cudaFuncSetAttribute(rules_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+      CK(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+      carveout_set[dev] = true;
+    }
+  }
+  const bool prof_r = S->prof_on && S->prof_n < PROF_MAX;
+  if (prof_r) CK(cudaEventRecord(S->prof_ev_r[2 * S->prof_n], S->hi));
   rules_kernel<G><<<blocks, BLOCK_THREADS, 0, S->hi>>>(p);
   CK(cudaGetLastError());
+  if (prof_r) CK(cudaEventRecord(S->prof_ev_r[2 * S->prof_n + 1], S->hi));
   CK(cudaEventRecord(S->rules_done[b], S->hi));
   CK(cudaStreamWaitEvent(st, S->rules_done[b], 0));
   int rc = after_rules();
@@ -704,25 +722,31 @@ int fpc_profile_enable(int on) {
   if (on && S->prof_ev.empty()) {
     S->prof_ev.resize(2 * PROF_MAX);
     for (auto &e : S->prof_ev) CK(cudaEventCreate(&e));
+    S->prof_ev_r.resize(2 * PROF_MAX);
+    for (auto &e : S->prof_ev_r) CK(cudaEventCreate(&e));
   }
   S->prof_on = on != 0;
   S->prof_n = 0;
   return FPC_OK;
 }
 
-int fpc_profile_read(int *launches, double *expand_ms) {
+int fpc_profile_read(int *launches, double *expand_ms, double *rules_ms) {
   SideState *S = nullptr;
   int rc = side_state(&S, 0, nullptr);
   if (rc != FPC_OK) return rc;
   CK(cudaStreamSynchronize(S->side));
-  double total = 0;
+  CK(cudaStreamSynchronize(S->hi));
+  double total = 0, total_r = 0;
   for (int i = 0; i < S->prof_n; ++i) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, S->prof_ev[2 * i], S->prof_ev[2 * i + 1]));
     total += ms;
+    CK(cudaEventElapsedTime(&ms, S->prof_ev_r[2 * i], S->prof_ev_r[2 * i + 1]));
+    total_r += ms;
   }
   if (launches) *launches = S->prof_n;
   if (expand_ms) *expand_ms = total;
+  if (rules_ms) *rules_ms = total_r;
   return FPC_OK;
 }
 

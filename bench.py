@@ -277,8 +277,8 @@ def run_ours(args) -> None:
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     import ctypes
-    ex_n, ex_ms = ctypes.c_int(0), ctypes.c_double(0.0)
-    _lib.check(L.fpc_profile_read(ctypes.byref(ex_n), ctypes.byref(ex_ms)))
+    ex_n, ex_ms, ru_ms = ctypes.c_int(0), ctypes.c_double(0.0), ctypes.c_double(0.0)
+    _lib.check(L.fpc_profile_read(ctypes.byref(ex_n), ctypes.byref(ex_ms), ctypes.byref(ru_ms)))
     _lib.check(L.fpc_profile_enable(0))
 
     # rules only (movegen + legal filter + result + make, no dense tensors): the integer-bound part
@@ -372,6 +372,7 @@ def run_ours(args) -> None:
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "expand_kernel", "bytes_per_launch": N_GAMES * DENSE_BYTES_PER_POSITION,
                          "avg_launch_ms": ex_avg_ms, "launches_timed": ex_n.value,
+                         "rules_kernel_avg_launch_ms": ru_ms.value / max(ex_n.value, 1),
                          "whole_step": {"bytes": N_GAMES * BYTES_PER_POSITION, "ms": per_gpu_ms, "achieved": step_gbs,
                                         "frac": step_gbs / peak,
                                         "note": "rules_kernel + expand_kernel pipelined; 113,312 B per position over "

@@ -99,11 +99,11 @@ int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_
 #define FPC_FLAG_ASYNC_DENSE 1
 int fpc_join(void *stream);
 
-/* Measurement hook: time every expand_kernel launch with CUDA events on the stream it runs on (up to
- * 4096 launches per enable).  fpc_profile_read waits for that stream and returns the number of timed
- * launches and the sum of their durations in milliseconds. */
+/* Measurement hook: time every expand_kernel and (dense-path) rules_kernel launch with CUDA events on the
+ * streams they run on (up to 4096 launches per enable).  fpc_profile_read waits for those streams and
+ * returns the number of timed launches and the summed durations in milliseconds. */
 int fpc_profile_enable(int on);
-int fpc_profile_read(int *launches, double *expand_ms);
+int fpc_profile_read(int *launches, double *expand_ms, double *rules_ms);
 
 /* Board::GetEncodedStates alone (no move generation). */
 int fpc_encode(int R, const uint8_t *d_boards, int n, const int32_t *d_k, int k_all, float *d_planes,
