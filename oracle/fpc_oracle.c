@@ -652,6 +652,30 @@ uint64_t fpo_bench_playout(int R, int IA, const uint8_t *start, uint64_t seed, u
 }
 
 /* ------------------------------------------------------------------ PUCT ----------------- */
+/* Order-independent checksum over whole playouts of games first_game .. first_game + n_games - 1: the sum over
+ * every visited position of  n_legal*4 + result + ((move * 0x9E3779B97F4A7C15) >> 40),  move = the move played
+ * (0 where the game ended).  The -m gpu soak test recomputes it from the device's per-step outputs. */
+uint64_t fpo_playout_checksum(int R, int IA, const uint8_t *start, uint64_t seed, uint64_t first_game, int n_games,
+                              int max_plies, uint64_t *positions_out) {
+  Geo g = geo(R, IA);
+  uint64_t positions = 0, sum = 0;
+  uint8_t cur[256], nxt[256];
+  for (int i = 0; i < n_games; ++i) {
+    memcpy(cur, start, (size_t)g.rec);
+    for (int p = 0; p < max_plies; ++p) {
+      int n = 0;
+      uint64_t mv = 0;
+      int res = fpo_playout_step(R, IA, cur, seed, first_game + (uint64_t)i, (uint64_t)p, nxt, &n, &mv);
+      ++positions;
+      sum += (uint64_t)n * 4 + (uint64_t)res + ((mv * 0x9E3779B97F4A7C15ull) >> 40);
+      if (res != IN_PROGRESS) break;
+      memcpy(cur, nxt, (size_t)g.rec);
+    }
+  }
+  if (positions_out) *positions_out = positions;
+  return sum;
+}
+
 /* src/cpp/node.{h,cpp}: a tree of nodes over one game, children stored contiguously.
  * Arrays are caller-owned (numpy); node 0 is the root (visit_count 1, src/py/mcts.py:30). */
 typedef struct {

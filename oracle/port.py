@@ -53,6 +53,9 @@ def lib():
         L.fpo_bench_playout.argtypes = [C.c_int, C.c_int, _u8p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
                                         C.POINTER(C.c_uint64)]
         L.fpo_bench_playout.restype = C.c_uint64
+        L.fpo_playout_checksum.argtypes = [C.c_int, C.c_int, _u8p, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
+                                           C.POINTER(C.c_uint64)]
+        L.fpo_playout_checksum.restype = C.c_uint64
         L.fpo_select_child.argtypes = [_i32p, _i32p, _i32p, _f64p, _f64p, C.c_int, C.c_double]
         L.fpo_backpropagate.argtypes = [_i32p, _i32p, _f64p, C.c_int, C.c_float]
         _LIB = L
@@ -156,6 +159,12 @@ class Oracle:
             cur = nxt
         return dict(n=len(recs), recs=np.stack(recs), n_legal=np.array(nl, dtype=np.int32),
                     result=np.array(rs, dtype=np.int32), moves=np.array(mv, dtype=np.uint64))
+
+    def playout_checksum(self, start, seed, first_game, n_games, max_plies):
+        pos = C.c_uint64(0)
+        chk = self.L.fpo_playout_checksum(self.R, self.IA, np.ascontiguousarray(start), seed, first_game, n_games,
+                                          max_plies, C.byref(pos))
+        return int(chk), int(pos.value)
 
     def bench_playout(self, start, seed, first_game, min_positions, max_plies):
         chk = C.c_uint64(0)

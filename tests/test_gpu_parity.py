@@ -326,6 +326,36 @@ def test_async_dense_pipeline_matches_sync():
     assert np.array_equal(a.mask_buffer()[:256].cpu().numpy(), o.mask(recs))
 
 
+def test_million_position_playout_checksum():
+    """BASELINE.json configs[1] at full size: 4,096 games played to the end (or 300 plies) on the device, > 1 M
+    positions; the order-independent checksum over every position's (n_legal, result, move played) must equal
+    the oracle's over the same games (oracle/fpc_oracle.c fpo_playout_checksum, 8 host threads)."""
+    from concurrent.futures import ThreadPoolExecutor
+    R, n, max_plies = 14, 4096, 300
+    o = oracle_for(R)
+    start = start_record("STANDARD", castling=True)
+    env = BatchedEnv(R, n)
+    env.reset_playout(start)
+    total = torch.zeros((), dtype=torch.int64, device="cuda")
+    positions = torch.zeros((), dtype=torch.int64, device="cuda")
+    K = torch.tensor(0x9E3779B97F4A7C15 - (1 << 64), dtype=torch.int64, device="cuda")
+    for _ in range(max_plies):
+        first = env.game < n  # slots still playing their first game (re-seeded slots get ids >= n)
+        env.playout_step(seed=SEED, max_plies=max_plies, planes=False, mask=False, chosen=True)
+        v = env.counts.long() * 4 + (env.status.long() & 3) + (((env.chosen * K) >> 40) & 0xFFFFFF)
+        total += torch.where(first, v, torch.zeros_like(v)).sum()
+        positions += first.sum()
+    torch.cuda.synchronize()
+    assert not bool((env.game < n).any())
+    chunks = [(g0, 256) for g0 in range(0, n, 256)]
+    with ThreadPoolExecutor(8) as ex:  # ctypes releases the GIL
+        parts = list(ex.map(lambda c: o.playout_checksum(start, SEED, c[0], c[1], max_plies), chunks))
+    want = sum(p[0] for p in parts) & ((1 << 64) - 1)
+    want_pos = sum(p[1] for p in parts)
+    assert int(positions.item()) == want_pos and want_pos > 1_000_000
+    assert int(total.item()) & ((1 << 64) - 1) == want
+
+
 def test_dlpack_handoff_is_zero_copy():
     R, n = 8, 64
     env = BatchedEnv(R, n)
