@@ -58,3 +58,21 @@ class InferenceNet:
         x = planes.to(self.dtype).contiguous(memory_format=torch.channels_last)
         logits, value = self.net(x)
         return logits.float(), value.float()
+
+
+class AutocastNet:
+    """Inference view of a model that is also being trained: eval-mode forward under bf16 autocast, weights
+    untouched (fp32), f32 logits / values out."""
+
+    def __init__(self, net: PolicyValueNet):
+        self.net = net
+        self.device = net.device
+
+    @torch.no_grad()
+    def __call__(self, planes: torch.Tensor):
+        was_training = self.net.training
+        self.net.eval()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits, value = self.net(planes)
+        self.net.train(was_training)
+        return logits.float(), value.float()
