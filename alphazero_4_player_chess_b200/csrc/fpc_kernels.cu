@@ -195,16 +195,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_c
           from = s.plist[item >> 2];
           gen_item<G>(s.mb, from, item & 3, lo, hi, kind);
         }
-        const int cnt = lo.cnt + hi.cnt;
-        // exclusive prefix sum of cnt over the warp
-        int incl = cnt;
+        const int cnt = lo.cnt + hi.cnt;  // <= 26: two rays of at most 13 squares
+        // exclusive prefix sum of cnt over the warp, bit-sliced over five ballots: votes and popcounts
+        // only, no trip through the shuffle / shared-memory pipe
+        int excl = 0, total = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(FULL, incl, o);
-          if (lane >= o) incl += v;
+        for (int bit = 0; bit < 5; ++bit) {
+          const unsigned b = __ballot_sync(FULL, (cnt >> bit) & 1);
+          excl += __popc(b & lt_mask) << bit;
+          total += __popc(b) << bit;
         }
-        const int total = __shfl_sync(FULL, incl, 31);
-        int at = n_pseudo + incl - cnt;
+        int at = n_pseudo + excl;
         if (n_pseudo + total > MAX_MOVES) {
           overflow = true;
         } else {

@@ -73,7 +73,8 @@ int fpc_move_flat_index(int R, uint64_t move);      /* Move::GetFlatIndex, -1 wh
 
 /* ---- device-pointer batch operations ------------------------------------------------------ */
 
-/* The fused observation kernel.  For each of n board records:
+/* Observation of a batch (rules_kernel, plus expand_kernel when a dense tensor is asked for).  d_planes / d_mask
+ * must be 16-byte aligned.  For each of n board records:
  *   legal moves      = fpchess::Board::GetLegalMoves (src/cpp/board.cpp:94-118) over
  *                      chess::Board::GetPseudoLegalMoves2 (engine/board.cpp:846-889)
  *   status           = chess::Board::GetGameResult (engine/board.cpp:891-939), order-independent
