@@ -13,8 +13,9 @@ REFERENCE ITSELF in the build container (it cannot travel to the GPU box):
                       TakeAction boards for full and index-built moves, the ParseActionspace
                       permutation, heuristics.
   mcts_R<R>.npz       the reference's `MCTS.search` (`src/py/mcts.py`) on the reference binding with
-                      the deterministic stand-in network of tests/golden/fake_net.py: root children,
-                      priors, visit counts and value sums per game.
+                      the deterministic stand-in network of tests/golden/fake_net.py: per game the root's
+                      children (flat action indices, visit counts), the root's visit count and the
+                      number of nodes in the tree (the binding exposes neither priors nor value sums).
 
 usage:  python tests/golden/make_golden.py            # everything (needs /root/reference)
         python tests/golden/make_golden.py --binding 14   # (internal) one binding geometry
