@@ -18,6 +18,25 @@ __global__ void __launch_bounds__(128) fill(float4 *out, unsigned long long n16,
   }
 }
 
+// TMA variant: one elected thread per CTA streams zeros with cp.async.bulk shared->global (16 KB per op)
+constexpr int ZT = 16384;
+__global__ void __launch_bounds__(128) fill_tma(uint8_t *out, unsigned long long bytes) {
+  extern __shared__ __align__(128) uint8_t z[];
+  for (int i = threadIdx.x; i < ZT / 16; i += 128) reinterpret_cast<uint4 *>(z)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const unsigned long long n = (bytes + ZT - 1) / ZT;
+  const uint32_t src = (uint32_t)__cvta_generic_to_shared(z);
+  for (unsigned long long c = blockIdx.x; c < n; c += gridDim.x) {
+    const unsigned long long left = bytes - c * ZT;
+    const uint32_t sz = left < ZT ? (uint32_t)left : ZT;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + c * ZT), "r"(src), "r"(sz) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(128) co(int iters, int *sink) {
   __shared__ uint8_t sm[21000];
   for (int i = threadIdx.x; i < 21000; i += 128) sm[i] = (uint8_t)(i * 7 + 1);
@@ -46,7 +65,7 @@ int main() {
   CUdevResource all;
   DRV(cuDeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
   printf("device SMs: %u\n", all.sm.smCount);
-  for (unsigned n1 : {32u, 48u, 64u, 80u}) {
+  for (unsigned n1 : {32u, 48u, 64u, 80u, 96u}) {
     CUdevResource part[1], rest;
     unsigned groups = 1;
     DRV(cuDevSmResourceSplitByCount(part, &groups, &all, &rest, 0, n1));
@@ -75,6 +94,28 @@ int main() {
       cudaDeviceSynchronize();
       float f, c; cudaEventElapsedTime(&f, e0, e1); cudaEventElapsedTime(&c, h0, h1);
       if (r >= 3) { fsum += f; csum += c; }
+    }
+    {
+      cudaFuncSetAttribute(fill_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, ZT);
+      for (int per_sm : {2, 4, 8}) {
+        float tsum = 0;
+        for (int r = 0; r < reps + 3; ++r) {
+          cudaDeviceSynchronize();
+          cudaEventRecord(e0, (cudaStream_t)sB); fill_tma<<<nB * per_sm, 128, ZT, (cudaStream_t)sB>>>((uint8_t *)buf, bytes); cudaEventRecord(e1, (cudaStream_t)sB);
+          cudaDeviceSynchronize(); cudaEventElapsedTime(&ms, e0, e1); if (r >= 3) tsum += ms;
+        }
+        printf("   TMA fill alone on %3u SMs, %d CTAs/SM: %6.1f us (%.0f GB/s)\n", nB, per_sm, tsum / reps * 1e3, bytes / (tsum / reps * 1e-3) / 1e9);
+      }
+      float tsum = 0, csum2 = 0;
+      for (int r = 0; r < reps + 3; ++r) {
+        cudaDeviceSynchronize();
+        cudaEventRecord(h0, (cudaStream_t)sA); co<<<1024, 128, 0, (cudaStream_t)sA>>>(iters, sink); cudaEventRecord(h1, (cudaStream_t)sA);
+        cudaEventRecord(e0, (cudaStream_t)sB); fill_tma<<<nB * 4, 128, ZT, (cudaStream_t)sB>>>((uint8_t *)buf, bytes); cudaEventRecord(e1, (cudaStream_t)sB);
+        cudaDeviceSynchronize();
+        float f, c; cudaEventElapsedTime(&f, e0, e1); cudaEventElapsedTime(&c, h0, h1);
+        if (r >= 3) { tsum += f; csum2 += c; }
+      }
+      printf("   TMA fill + co together: co %6.1f us, fill %6.1f us (%.0f GB/s)\n", csum2 / reps * 1e3, tsum / reps * 1e3, bytes / (tsum / reps * 1e-3) / 1e9);
     }
     printf("co on %3u SMs, fill on %3u SMs: fill alone %6.1f us (%.0f GB/s); together: co %6.1f us, fill %6.1f us (%.0f GB/s)\n", nA, nB,
            falone / reps * 1e3, bytes / (falone / reps * 1e-3) / 1e9, csum / reps * 1e3, fsum / reps * 1e3, bytes / (fsum / reps * 1e-3) / 1e9);
