@@ -76,5 +76,32 @@ int main() {
     printf("%-28s co alone ~30 us; together: co %6.1f us, fill %6.1f us (%.0f GB/s)\n", names[mode], mode ? cosum / reps * 1e3 : 0.0f,
            sum / reps * 1e3, bytes / (sum / reps * 1e-3) / 1e9);
   }
+  // the same co-kernels beside cudaMemsetAsync (does the driver's memset run on the SMs or on a copy engine?)
+  for (int mode = 0; mode <= 4; mode += 3) {
+    int iters = 30;
+    float co_ms = 0;
+    if (mode) {
+      for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(h0, hi); co<<<1024, 128, 0, hi>>>(mode, iters, sink); cudaEventRecord(h1, hi);
+        cudaDeviceSynchronize(); cudaEventElapsedTime(&co_ms, h0, h1);
+        iters = (int)(iters * 0.030f / co_ms) + 1;
+      }
+    }
+    float fill_ms = 0, sum = 0, cosum = 0;
+    const int reps = 20;
+    for (int r = 0; r < reps + 3; ++r) {
+      cudaDeviceSynchronize();
+      cudaEventRecord(go, lo);
+      cudaStreamWaitEvent(hi, go, 0);
+      if (mode) { cudaEventRecord(h0, hi); co<<<1024, 128, 0, hi>>>(mode, iters, sink); cudaEventRecord(h1, hi); }
+      cudaEventRecord(e0, lo); cudaMemsetAsync(buf, 0, bytes, lo); cudaEventRecord(e1, lo);
+      cudaDeviceSynchronize();
+      cudaEventElapsedTime(&fill_ms, e0, e1);
+      if (mode) cudaEventElapsedTime(&co_ms, h0, h1);
+      if (r >= 3) { sum += fill_ms; cosum += co_ms; }
+    }
+    printf("cudaMemsetAsync beside %-28s: co %6.1f us, memset %6.1f us (%.0f GB/s)\n", names[mode], mode ? cosum / reps * 1e3 : 0.0f,
+           sum / reps * 1e3, bytes / (sum / reps * 1e-3) / 1e9);
+  }
   return 0;
 }
