@@ -15,6 +15,7 @@ FPC_OK, FPC_ERR_ARG, FPC_ERR_CUDA, FPC_ERR_MOVE, FPC_ERR_OVERFLOW = 0, -1, -2, -
 STATUS_RESULT_MASK, STATUS_IN_CHECK, STATUS_CAN_TAKE_KING = 0x3, 0x100, 0x200
 STATUS_OVERFLOW, STATUS_FINISHED = 0x400, 0x800
 FLAG_ASYNC_DENSE = 1
+FLAG_INCREMENTAL = 2
 
 _vp, _i, _u64 = C.c_void_p, C.c_int, C.c_uint64
 

@@ -66,6 +66,7 @@ template <class G>
 struct alignas(16) WarpScratch {
   uint32_t mask_bits[G::MASK_STRIDE];    // legal-move mask, 1 bit per action
   uint32_t plane_bits[G::PLANE_STRIDE];  // input planes, 1 bit per cell
+  uint16_t list[368];             // the ones this call leaves in the dense tensors (fpc_kernels.cu LIST_*)
   uint32_t moves[MAX_MOVES + 4];  // compact moves: key<<14 | castle<<8 | to_mb, key = flat*8 + promo
   uint8_t mb[1024];               // mailbox board in four layouts (see put_cell): rows, columns, diagonals, anti-diagonals
   uint8_t rec[256];               // raw record staging (in and out)

@@ -33,6 +33,12 @@ struct ObserveParams {
   const int32_t *k;     // [n] or null
   int k_all;            // -1: own turn
   uint32_t *mask_bits;  // [n][MASK_WORDS] or null: legal-move mask, 1 bit per action
+  // Record of the ones a dense call leaves in the caller's tensors: [n][LIST_STRIDE] u16 (in: what the tensors
+  // hold now, out: what they hold after this call).  With inc_planes / inc_mask set the tensors are updated in
+  // place -- previous ones cleared, current ones set -- instead of being rewritten (FPC_FLAG_INCREMENTAL).
+  uint16_t *lists;
+  int list_cells, list_flats;  // which halves of the record this call maintains (planes / mask requested)
+  float *inc_planes, *inc_mask;
   // playout
   int playout;
   uint64_t seed;
@@ -51,6 +57,10 @@ struct ObserveParams {
 // per game); expand_kernel streams the bits out as f32.  The two kernels run on different streams so
 // that the expansion of one batch overlaps the integer work of the next (FPC_FLAG_ASYNC_DENSE,
 // fpc_join).
+
+// List of one game (u16 units): [0] number of mask entries, [1] number of plane entries, [2, 66) plane cell
+// indices ch*R*R + row*R + col (already rotated), [66, 366) flat action indices; 368 u16 = 736 B.
+constexpr int LIST_PLANES = 2, LIST_FLAT = 66, LIST_STRIDE = 368;
 
 #define CK(expr)                                   \
   do {                                             \
@@ -138,12 +148,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_c
 
   // ---- unpack into the mailbox + piece scan: king squares, the mover's piece list, the
   //      input-plane bits (src/cpp/board.cpp:318-344) ------------------------------------------
+  const bool want_planes = P.plane_bits || (P.lists && P.list_cells);
   int rot = 0;
-  if (P.plane_bits) {
+  if (want_planes) {
     rot = P.k ? P.k[g] : (P.k_all < 0 ? turn : P.k_all);
     rot &= 3;
   }
-  int np = 0;
+  int np = 0, n_cells = 0;
   {
     const HalfRow<G> hr(lane);
 #pragma unroll
@@ -163,19 +174,26 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_c
         if (idx < 64) s.plist[idx] = (uint8_t)G::mb(r, c);
       }
       np += __popc(b);
-      if (P.plane_bits && present(p)) {
-        // ch = ((color - turn) mod 4)*6 + type - 1, -1 wrapping to 23 (src/cpp/board.cpp:336)
-        int ch = ((color_of(p) - turn) & 3) * 6 + type_of(p) - 1;
-        if (ch < 0) ch += 24;
-        // torch.rot90(k) on the last two dims: one quarter turn sends (r,c) -> (R-1-c, r)
-        const int rr = rot == 0 ? r : (rot == 1 ? G::R - 1 - c : (rot == 2 ? G::R - 1 - r : c));
-        const int cc = rot == 0 ? c : (rot == 1 ? r : (rot == 2 ? G::R - 1 - c : G::R - 1 - r));
-        const int bit = ch * G::NSQ + rr * G::R + cc;
-        atomicOr(&s.plane_bits[bit >> 5], 1u << (bit & 31));
+      if (want_planes) {
+        const unsigned pb = __ballot_sync(FULL, present(p));
+        if (present(p)) {
+          // ch = ((color - turn) mod 4)*6 + type - 1, -1 wrapping to 23 (src/cpp/board.cpp:336)
+          int ch = ((color_of(p) - turn) & 3) * 6 + type_of(p) - 1;
+          if (ch < 0) ch += 24;
+          // torch.rot90(k) on the last two dims: one quarter turn sends (r,c) -> (R-1-c, r)
+          const int rr = rot == 0 ? r : (rot == 1 ? G::R - 1 - c : (rot == 2 ? G::R - 1 - r : c));
+          const int cc = rot == 0 ? c : (rot == 1 ? r : (rot == 2 ? G::R - 1 - c : G::R - 1 - r));
+          const int bit = ch * G::NSQ + rr * G::R + cc;
+          if (P.plane_bits) atomicOr(&s.plane_bits[bit >> 5], 1u << (bit & 31));
+          const int idx = n_cells + __popc(pb & lt_mask);
+          if (idx < 64) s.list[LIST_PLANES + idx] = (uint16_t)bit;
+        }
+        n_cells += __popc(pb);
       }
     }
   }
   if (np > 64) np = 64;
+  if (n_cells > 64) n_cells = 64;
   __syncwarp();
 
   int n_legal = 0, status = 0;
@@ -274,7 +292,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_c
     if (P.playout && result == 0)
       pick = (uint32_t)(((mix64(P.seed, game_id, (uint64_t)ply) >> 32) * (uint64_t)n_legal) >> 32);
     const bool want_lists = P.moves || P.flat;
-    if (want_lists || P.mask_bits || P.playout) {
+    const bool want_flats = P.lists && P.list_flats;
+    if (want_lists || P.mask_bits || P.playout || want_flats) {
       // pad to a multiple of four with keys above every real one: the rank loop compares four keys per load
       if (lane < 4) s.moves[n_legal + lane] = 0xffffffffu;
       __syncwarp();
@@ -284,6 +303,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_c
           const uint32_t mv = s.moves[i];
           const uint32_t flat = mv >> 17;
           if (P.mask_bits) atomicOr(&s.mask_bits[flat >> 5], 1u << (flat & 31));
+          if (want_flats) s.list[LIST_FLAT + i] = (uint16_t)flat;
           if (want_lists || P.playout) {
             int rank = 0;
             for (int j = 0; j < n_legal; j += 4) {
@@ -311,6 +331,38 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_c
   if (P.mask_bits)
     for (int i = lane; i < G::MASK_STRIDE / 4; i += 32)
       reinterpret_cast<uint4 *>(P.mask_bits + (size_t)g * G::MASK_STRIDE)[i] = reinterpret_cast<const uint4 *>(s.mask_bits)[i];
+
+  // ---- the record of ones / in-place update of the dense tensors (FPC_FLAG_INCREMENTAL) ---------
+  if (P.lists) {
+    uint16_t *gl = P.lists + (size_t)g * LIST_STRIDE;
+    const int new_flats = P.list_flats ? n_legal : 0, new_cells = P.list_cells ? n_cells : 0;
+    if (P.inc_planes || P.inc_mask) {
+      const int old_flats = gl[0], old_cells = gl[1];
+      if (P.inc_planes) {
+        float *dst = P.inc_planes + (size_t)g * G::SSZ;
+        for (int i = lane; i < old_cells; i += 32) dst[gl[LIST_PLANES + i]] = 0.0f;
+      }
+      if (P.inc_mask) {
+        float *dst = P.inc_mask + (size_t)g * G::ASZ;
+        for (int i = lane; i < old_flats; i += 32) dst[gl[LIST_FLAT + i]] = 0.0f;
+      }
+      __syncwarp();  // warp-level memory ordering: every clear precedes every set (a cell may be in both lists)
+      if (P.inc_planes) {
+        float *dst = P.inc_planes + (size_t)g * G::SSZ;
+        for (int i = lane; i < new_cells; i += 32) dst[s.list[LIST_PLANES + i]] = 1.0f;
+      }
+      if (P.inc_mask) {
+        float *dst = P.inc_mask + (size_t)g * G::ASZ;
+        for (int i = lane; i < new_flats; i += 32) dst[s.list[LIST_FLAT + i]] = 1.0f;
+      }
+    }
+    if (lane == 0) {
+      s.list[0] = (uint16_t)new_flats;
+      s.list[1] = (uint16_t)new_cells;
+    }
+    __syncwarp();
+    for (int i = lane; i < LIST_STRIDE / 8; i += 32) reinterpret_cast<uint4 *>(gl)[i] = reinterpret_cast<const uint4 *>(s.list)[i];
+  }
 
   // ---- playout: play the chosen move or re-seed the slot ------------------------------------
   if (P.playout) {
@@ -494,6 +546,17 @@ struct SideState {
   size_t bits_words = 0;
   int parity = 0;
   int last = -1;  // buffer of the most recent expansion (fpc_join)
+  // Dense tensors whose content is known exactly: the list of ones the latest call left in them
+  // (FPC_FLAG_INCREMENTAL updates such tensors in place instead of rewriting them).
+  struct Tracked {
+    const float *planes = nullptr, *mask = nullptr;
+    int n = 0, R = 0;
+    uint16_t *lists = nullptr;
+    size_t lists_games = 0;
+    unsigned long long stamp = 0;
+  };
+  Tracked tracked[4];
+  unsigned long long stamp = 0;
   // optional CUDA-event timing of expand_kernel on its own stream (fpc_profile_enable / _read)
   bool prof_on = false;
   int prof_n = 0;
@@ -542,6 +605,35 @@ struct DenseOut {
   int flags;
 };
 
+// The record slot of a (planes, mask, n, R) output set: an existing one (content known: *known = true) or the least
+// recently used one, re-targeted (content unknown until a full dense call has run).
+static int tracked_slot(SideState *S, const DenseOut &d, int n, int R, cudaStream_t st, SideState::Tracked **out, bool *known) {
+  SideState::Tracked *hit = nullptr, *lru = &S->tracked[0];
+  for (auto &t : S->tracked) {
+    if (t.lists && t.planes == d.planes && t.mask == d.mask && t.n == n && t.R == R) hit = &t;
+    if (t.stamp < lru->stamp) lru = &t;
+  }
+  *known = hit != nullptr;
+  SideState::Tracked *t = hit ? hit : lru;
+  if (!hit) {
+    if (t->lists_games < (size_t)n) {
+      if (t->lists) {
+        CK(cudaStreamSynchronize(st));
+        CK(cudaStreamSynchronize(S->side));
+        CK(cudaStreamSynchronize(S->hi));
+        cudaFree(t->lists);
+        t->lists = nullptr;
+      }
+      CK(cudaMalloc(&t->lists, (size_t)n * LIST_STRIDE * sizeof(uint16_t)));
+      t->lists_games = (size_t)n;
+    }
+    t->planes = d.planes, t->mask = d.mask, t->n = n, t->R = R;
+  }
+  t->stamp = ++S->stamp;
+  *out = t;
+  return FPC_OK;
+}
+
 // rules_kernel on the caller's stream; expand_kernel on the side stream once the rules kernel has
 // written the bit sets.  Unless FPC_FLAG_ASYNC_DENSE is set the caller's stream then waits for the
 // expansion.  after_rules (may be a no-op) runs right after the rules kernel is enqueued: the
@@ -558,6 +650,24 @@ static int launch_observe(ObserveParams p, DenseOut d, cudaStream_t st, F after_
     const size_t pw = (size_t)p.n * G::PLANE_STRIDE, mw = (size_t)p.n * G::MASK_STRIDE;
     int rc = side_state(&S, pw + mw, st);
     if (rc != FPC_OK) return rc;
+    SideState::Tracked *trk = nullptr;
+    bool known = false;
+    rc = tracked_slot(S, d, p.n, G::R, st, &trk, &known);
+    if (rc != FPC_OK) return rc;
+    p.lists = trk->lists;
+    p.list_cells = d.planes != nullptr;
+    p.list_flats = d.mask != nullptr;
+    if ((d.flags & FPC_FLAG_INCREMENTAL) && known) {
+      // the tensors hold exactly the recorded ones: clear those, set the new ones, no expansion.  A still running
+      // expansion into the same tensors (an earlier FPC_FLAG_ASYNC_DENSE call) must finish first.
+      if (S->last >= 0) CK(cudaStreamWaitEvent(st, S->expand_done[S->last], 0));
+      p.inc_planes = d.planes;
+      p.inc_mask = d.mask;
+      const int blocks_inc = (p.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+      rules_kernel<G><<<blocks_inc, BLOCK_THREADS, 0, st>>>(p);
+      CK(cudaGetLastError());
+      return after_rules();
+    }
     b = S->parity;
     S->parity ^= 1;
     p.plane_bits = d.planes ? S->bits[b] : nullptr;

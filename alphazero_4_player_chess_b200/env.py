@@ -105,7 +105,7 @@ class BatchedEnv:
             check(self.L.fpc_join(self._stream()))
 
     def observe(self, planes: bool = True, mask: bool = True, moves: bool = False, flat: bool = False,
-                k: int | torch.Tensor = -1, async_dense: bool = False):
+                k: int | torch.Tensor = -1, async_dense: bool = False, incremental: bool = False):
         """Legal moves / result / planes / mask of every game (one fused kernel launch)."""
         with torch.cuda.device(self.device):
             d_k = k if isinstance(k, torch.Tensor) else None
@@ -114,7 +114,8 @@ class BatchedEnv:
                 _ptr(self.moves_buffer() if moves else None), _ptr(self.flat_buffer() if flat else None),
                 self.counts.data_ptr(), self.status.data_ptr(),
                 _ptr(self.planes_buffer() if planes else None), _ptr(d_k), -1 if d_k is not None else int(k),
-                _ptr(self.mask_buffer() if mask else None), int(async_dense), self._stream()))
+                _ptr(self.mask_buffer() if mask else None), int(async_dense) | (2 if incremental else 0),
+                self._stream()))
         return self
 
     def encode(self, k: int | torch.Tensor = -1) -> torch.Tensor:
@@ -147,7 +148,7 @@ class BatchedEnv:
 
     def playout_step(self, seed: int = 0x5EED, max_plies: int = 2048, game_stride: int | None = None,
                      planes: bool = True, mask: bool = True, k: int = -1, chosen: bool = False,
-                     async_dense: bool = False) -> None:
+                     async_dense: bool = False, incremental: bool = False) -> None:
         """One ply for every game slot (BASELINE.json configs[1]); finished slots are re-seeded."""
         stride = self.n if game_stride is None else game_stride
         with torch.cuda.device(self.device):
@@ -156,5 +157,5 @@ class BatchedEnv:
                 self.start.data_ptr(), max_plies, stride, _ptr(self.chosen if chosen else None),
                 self.counts.data_ptr(), self.status.data_ptr(),
                 _ptr(self.planes_buffer() if planes else None), None, int(k),
-                _ptr(self.mask_buffer() if mask else None), self.counters.data_ptr(), int(async_dense),
-                self._stream()))
+                _ptr(self.mask_buffer() if mask else None), self.counters.data_ptr(),
+                int(async_dense) | (2 if incremental else 0), self._stream()))

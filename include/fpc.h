@@ -100,6 +100,15 @@ int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_
 #define FPC_FLAG_ASYNC_DENSE 1
 int fpc_join(void *stream);
 
+/* FPC_FLAG_INCREMENTAL: resident dense tensors updated in place.  The library records which cells every dense
+ * call sets to 1.0 (per host thread and device, for the last few (d_planes, d_mask, n, R) output sets).  When a
+ * call carries this flag and its output set is one whose content is recorded, the rules kernel clears the
+ * previously set cells and sets the new ones -- some 120 scattered 4-byte stores per game instead of rewriting
+ * 113 KB -- and no expansion runs.  The result is bit-identical to a full rewrite PROVIDED nothing else wrote
+ * to the tensors since the previous call with the same output set; otherwise (or for an unknown output set) the
+ * call silently does the full rewrite.  Everything is ordered on `stream`. */
+#define FPC_FLAG_INCREMENTAL 2
+
 /* Measurement hook: time every expand_kernel and (dense-path) rules_kernel launch with CUDA events on the
  * streams they run on (up to 4096 launches per enable).  fpc_profile_read waits for those streams and
  * returns the number of timed launches and the summed durations in milliseconds. */

@@ -326,6 +326,45 @@ def test_async_dense_pipeline_matches_sync():
     assert np.array_equal(a.mask_buffer()[:256].cpu().numpy(), o.mask(recs))
 
 
+@pytest.mark.parametrize("name,R,n", [("STANDARD", 14, 777), ("THIRTEEN", 13, 130), ("EIGHT_SIMPLE", 8, 257)])
+def test_incremental_dense_update_equals_full_rewrite(name, R, n):
+    """FPC_FLAG_INCREMENTAL: resident planes / mask tensors updated in place (previous ones cleared, new ones set)
+    stay bit-identical to a full rewrite, step after step, across reloads, rotations and plane-only calls; an
+    output set the library has no record of falls back to the full rewrite."""
+    start = start_record(name, castling=True)
+    a, b = BatchedEnv(R, n), BatchedEnv(R, n)
+    a.reset_playout(start)
+    b.reset_playout(start)
+    a.planes_buffer().fill_(7.0)  # garbage: the first incremental call has no record and must rewrite everything
+    a.mask_buffer().fill_(7.0)
+    for step in range(45):
+        a.playout_step(seed=SEED, max_plies=30, planes=True, mask=True, incremental=True)
+        b.playout_step(seed=SEED, max_plies=30, planes=True, mask=True)
+        if step % 5 == 0 or step > 40:
+            torch.cuda.synchronize()
+            assert torch.equal(a.planes_buffer(), b.planes_buffer()), step
+            assert torch.equal(a.mask_buffer(), b.mask_buffer()), step
+    assert torch.equal(a.boards, b.boards)
+    # observe with a fixed rotation, then new boards in the same buffers
+    for k in (1, -1, 3):
+        a.observe(planes=True, mask=True, k=k, incremental=True)
+        b.observe(planes=True, mask=True, k=k)
+        assert torch.equal(a.planes_buffer(), b.planes_buffer()) and torch.equal(a.mask_buffer(), b.mask_buffer())
+    fresh = mixed_positions(name, n)
+    a.load(fresh)
+    b.load(fresh)
+    a.observe(planes=True, mask=True, incremental=True)
+    b.observe(planes=True, mask=True)
+    assert torch.equal(a.planes_buffer(), b.planes_buffer()) and torch.equal(a.mask_buffer(), b.mask_buffer())
+    # interleaving a full rewrite keeps the record valid
+    a.playout_step(seed=SEED, planes=True, mask=True)
+    a.playout_step(seed=SEED, planes=True, mask=True, incremental=True)
+    b.playout_step(seed=SEED, planes=True, mask=True)
+    b.playout_step(seed=SEED, planes=True, mask=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a.planes_buffer(), b.planes_buffer()) and torch.equal(a.mask_buffer(), b.mask_buffer())
+
+
 def test_million_position_playout_checksum():
     """BASELINE.json configs[1] at full size: 4,096 games played to the end (or 300 plies) on the device, > 1 M
     positions; the order-independent checksum over every position's (n_legal, result, move played) must equal

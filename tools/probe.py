@@ -30,6 +30,7 @@ timeit("playout mask only", lambda: env.playout_step(planes=False, mask=True))
 timeit("playout planes+mask", lambda: env.playout_step(planes=True, mask=True))
 timeit("playout planes+mask async", lambda: env.playout_step(planes=True, mask=True, async_dense=True))
 env.join()
+timeit("playout planes+mask incremental", lambda: env.playout_step(planes=True, mask=True, incremental=True))
 timeit("encode only", lambda: env.encode())
 timeit("observe planes+mask (no playout)", lambda: env.observe(planes=True, mask=True))
 timeit("observe mask", lambda: env.observe(planes=False, mask=True))
