@@ -42,7 +42,7 @@ SIGNATURES = {
     "fpc_playout_step": (_i, [_i, _vp, _i, _u64, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _vp, _vp, _i, _vp,
                               _vp, _i, _vp]),
     "fpc_tree_reset": (_i, [_vp, _vp, _vp]),
-    "fpc_tree_select": (_i, [_vp, _i, _vp, _vp]),
+    "fpc_tree_select": (_i, [_vp, _i, _vp, _i, _vp]),
     "fpc_tree_expand_backup": (_i, [_vp, _vp, _vp, _vp]),
     "fpc_ctx_create": (_vp, [_i, _i, _i]),
     "fpc_ctx_destroy": (None, [_vp]),

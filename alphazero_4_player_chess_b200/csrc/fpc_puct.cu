@@ -353,7 +353,7 @@ int fpc_tree_reset(const fpc_tree *t, const uint8_t *d_root_boards, void *stream
   return cuda_check(cudaGetLastError(), "tree_reset_kernel launch");
 }
 
-int fpc_tree_select(const fpc_tree *t, int batch_rotation, float *d_planes, void *stream) {
+int fpc_tree_select(const fpc_tree *t, int batch_rotation, float *d_planes, int flags, void *stream) {
   int rc = check_tree(t, "fpc_tree_select");
   if (rc != FPC_OK) return rc;
   if (t->n_games == 0) return FPC_OK;
@@ -367,7 +367,7 @@ int fpc_tree_select(const fpc_tree *t, int batch_rotation, float *d_planes, void
   }
   // legal moves + GetGameResult + planes of the leaf batch: the environment's rules kernel
   return fpc_observe(t->R, t->leaf_boards, t->n_games, nullptr, t->leaf_flat, t->leaf_counts, t->leaf_status, d_planes,
-                     t->k, 0, nullptr, 0, stream);
+                     t->k, 0, nullptr, flags, stream);
 }
 
 int fpc_tree_expand_backup(const fpc_tree *t, const float *d_logits, const float *d_values, void *stream) {

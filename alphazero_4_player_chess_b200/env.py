@@ -40,6 +40,7 @@ class BatchedEnv:
         self.chosen = torch.zeros(self.n, dtype=torch.int64, device=self.device)
         self._planes = None
         self._mask = None
+        self._dense_known = set()  # output sets (planes?, mask?) this env has fully written at least once
         self._moves = None
         self._flat = None
 
@@ -107,6 +108,8 @@ class BatchedEnv:
     def observe(self, planes: bool = True, mask: bool = True, moves: bool = False, flat: bool = False,
                 k: int | torch.Tensor = -1, async_dense: bool = False, incremental: bool = False):
         """Legal moves / result / planes / mask of every game (one fused kernel launch)."""
+        incremental = incremental and (planes, mask) in self._dense_known  # fresh buffers: full rewrite first
+        self._dense_known.add((planes, mask))
         with torch.cuda.device(self.device):
             d_k = k if isinstance(k, torch.Tensor) else None
             check(self.L.fpc_observe(
@@ -151,6 +154,8 @@ class BatchedEnv:
                      async_dense: bool = False, incremental: bool = False) -> None:
         """One ply for every game slot (BASELINE.json configs[1]); finished slots are re-seeded."""
         stride = self.n if game_stride is None else game_stride
+        incremental = incremental and (planes, mask) in self._dense_known
+        self._dense_known.add((planes, mask))
         with torch.cuda.device(self.device):
             check(self.L.fpc_playout_step(
                 self.R, self.boards.data_ptr(), self.n, seed, self.game.data_ptr(), self.ply.data_ptr(),

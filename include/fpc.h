@@ -196,8 +196,9 @@ int fpc_tree_reset(const fpc_tree *t, const uint8_t *d_root_boards, void *stream
  * materialise the leaf's board, run the rules kernel on the leaf batch (legal moves + GetGameResult)
  * and encode it into d_planes [n_games][24][R][R] (Board::GetEncodedStates).  batch_rotation != 0
  * reproduces the reference: every leaf is rotated by the colour of the first live leaf
- * (src/cpp/board.cpp:354-355); 0 rotates each leaf by its own side to move. */
-int fpc_tree_select(const fpc_tree *t, int batch_rotation, float *d_planes, void *stream);
+ * (src/cpp/board.cpp:354-355); 0 rotates each leaf by its own side to move.  flags: FPC_FLAG_INCREMENTAL updates
+ * d_planes in place (the network only reads it between two selects), see above. */
+int fpc_tree_select(const fpc_tree *t, int batch_rotation, float *d_planes, int flags, void *stream);
 
 /* MCTS.step after the network (mcts.py:66-79) + MCTS.expand (mcts.py:82-89) for every game with a
  * leaf: terminal leaf -> Backpropagate(0 | -1) and drop the root (node.cpp:33-43); otherwise
