@@ -31,6 +31,7 @@ SIGNATURES = {
     "fpc_state_space_size": (_i, [_i]),
     "fpc_move_from_flat": (_u64, [_i, _i]),
     "fpc_move_flat_index": (_i, [_i, _u64]),
+    "fpc_record_from_fen": (_i, [_i, C.c_char_p, _i, _vp]),
     "fpc_observe": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "fpc_join": (_i, [_vp]),
     "fpc_profile_enable": (_i, [_i]),

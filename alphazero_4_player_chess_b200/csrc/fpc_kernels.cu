@@ -826,6 +826,66 @@ int fpc_move_flat_index(int R, uint64_t move) {
   return plane * R * R + (from / R) * R + from % R;
 }
 
+int fpc_record_from_fen(int R, const char *fen, int honour_castling, uint8_t *h_record) {
+  if (!fpc_supported(R) || !fen || !h_record) return fail(FPC_ERR_ARG, "fpc_record_from_fen: bad argument");
+  const int nsq = R * R, rec = fpc_record_bytes(R);
+  std::string text;
+  for (const char *c = fen; *c; ++c)
+    if (*c != '\n' && *c != '\r' && *c != ' ') text += *c;
+  auto split = [](const std::string &str, char sep) {
+    std::vector<std::string> out;
+    size_t at = 0;
+    for (;;) {
+      const size_t next = str.find(sep, at);
+      out.push_back(str.substr(at, next == std::string::npos ? std::string::npos : next - at));
+      if (next == std::string::npos) break;
+      at = next + 1;
+    }
+    return out;
+  };
+  const std::vector<std::string> parts = split(text, '-');
+  if (parts.size() < 5) return fail(FPC_ERR_ARG, "FEN string has too few fields");
+  static const char turns[] = "RBYG";
+  const char *tp = parts[0].size() == 1 ? strchr(turns, parts[0][0]) : nullptr;
+  if (!tp || !*tp) return fail(FPC_ERR_ARG, "Invalid player character in FEN string");
+  memset(h_record, 0, rec);
+  memset(h_record, 0x18, nsq);
+  h_record[nsq] = (uint8_t)(tp - turns);
+  for (int c = 0; c < 4; ++c) h_record[nsq + 1 + c] = 0x80, h_record[nsq + 5 + c] = (uint8_t)nsq;
+  const std::vector<std::string> ks = split(parts[2], ','), qs = split(parts[3], ',');
+  if (ks.size() != 4) return fail(FPC_ERR_ARG, "Invalid kingside castling availability in FEN string");
+  if (qs.size() != 4) return fail(FPC_ERR_ARG, "Invalid queenside castling availability in FEN string");
+  if (honour_castling)
+    for (int c = 0; c < 4; ++c) h_record[nsq + 1 + c] = (uint8_t)(0x80 | ((ks[c] == "1") << 6) | ((qs[c] == "1") << 5));
+  const std::vector<std::string> rows = split(parts.back(), '/');
+  if ((int)rows.size() > R) return fail(FPC_ERR_ARG, "Too many rows in piece placement");
+  static const char colors[] = "rbyg", types[] = "PNBRQK";
+  for (int row = 0; row < (int)rows.size(); ++row) {
+    int col = 0;
+    for (const std::string &cell : split(rows[row], ',')) {
+      if (cell.empty()) return fail(FPC_ERR_ARG, "Empty column string in piece placement");
+      const char *cp = strchr(colors, cell[0]);
+      if (cp && *cp) {
+        const char *ty = cell.size() == 2 ? strchr(types, cell[1]) : nullptr;
+        if (!ty || !*ty) return fail(FPC_ERR_ARG, "Piece placement string for player must be of length 2");
+        if (col >= R) return fail(FPC_ERR_ARG, "Piece placement outside the board");
+        const int color = (int)(cp - colors), type = (int)(ty - types);
+        h_record[row * R + col] = (uint8_t)(0x80 | (color << 5) | (type << 2));
+        if (type == 5) h_record[nsq + 5 + color] = (uint8_t)(row * R + col);
+        ++col;
+      } else if (cell == "x") {
+        ++col;
+      } else {
+        char *end = nullptr;
+        const long n = strtol(cell.c_str(), &end, 10);
+        if (!end || *end || n <= 0) return fail(FPC_ERR_ARG, "Invalid number of empty spaces in piece placement");
+        col += (int)n;
+      }
+    }
+  }
+  return FPC_OK;
+}
+
 int fpc_profile_enable(int on) {
   SideState *S = nullptr;
   int rc = side_state(&S, 0, nullptr);

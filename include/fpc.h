@@ -71,6 +71,15 @@ int fpc_state_space_size(int R);    /* Board::state_space_size = 24*R*R */
 uint64_t fpc_move_from_flat(int R, int flat_index); /* Move(int flat_index), move.cpp:41-61 */
 int fpc_move_flat_index(int R, uint64_t move);      /* Move::GetFlatIndex, -1 where GetIndex throws */
 
+/* FEN -> board record (host-side, no device needed): the 4pchess-style FEN of src/py/start_fens.py as
+ * src/py/fen_parser.py:104-170 parses it -- fields split on '-': field 0 the side to move (R/B/Y/G), fields 2 / 3
+ * kingside / queenside castling availability "a,b,c,d" in colour order, last field the placement (rows split on
+ * '/', cells on ','; "rP" = red pawn ..., "x" = one skipped cell, an integer = that many empty cells).  The
+ * reference's Python path computes the castling rights and then drops them (fen_parser.py:137-140,170):
+ * honour_castling = 0 reproduces that (all rights off), 1 keeps the FEN's rights.  h_record receives
+ * fpc_record_bytes(R) bytes.  Returns FPC_ERR_ARG with the parser's message in fpc_last_error() on bad input. */
+int fpc_record_from_fen(int R, const char *fen, int honour_castling, uint8_t *h_record);
+
 /* ---- device-pointer batch operations ------------------------------------------------------ */
 
 /* Observation of a batch (rules_kernel, plus expand_kernel when a dense tensor is asked for).  d_planes / d_mask

@@ -54,3 +54,29 @@ def test_no_cpu_fallback_without_a_device():
     L = _lib.lib()
     assert not L.fpc_ctx_create(0, 14, 16)
     assert b"no usable CUDA device" in L.fpc_last_error()
+
+
+def test_fen_loader_matches_the_python_mirror_and_the_reference():
+    """fpc_record_from_fen (C++, host-only) == fen.py == the reference's own parser output (golden)."""
+    import numpy as np
+    from alphazero_4_player_chess_b200 import _lib
+    from alphazero_4_player_chess_b200.fen import START_FENS, record_from_fen
+    L = _lib.lib()
+    golden = os.path.join(ROOT, "tests", "golden")
+    for name, (fen, R) in START_FENS.items():
+        for castling in (0, 1):
+            out = np.zeros(L.fpc_record_bytes(R), dtype=np.uint8)
+            assert L.fpc_record_from_fen(R, fen.encode(), castling, out.ctypes.data) == 0, L.fpc_last_error()
+            assert np.array_equal(out, record_from_fen(fen, R, castling=bool(castling))), (name, castling)
+        path = os.path.join(golden, f"binding_R{R}.npz")
+        if os.path.exists(path):
+            z = np.load(path)
+            if f"start_{name}" in z.files:
+                out = np.zeros(L.fpc_record_bytes(R), dtype=np.uint8)
+                assert L.fpc_record_from_fen(R, fen.encode(), 0, out.ctypes.data) == 0
+                assert np.array_equal(out, z[f"start_{name}"]), name
+    out = np.zeros(208, dtype=np.uint8)
+    assert L.fpc_record_from_fen(14, b"Q-0,0,0,0-1,1,1,1-1,1,1,1-0,0,0,0-0-x", 0, out.ctypes.data) == _lib.FPC_ERR_ARG
+    assert b"Invalid player character" in L.fpc_last_error()
+    assert L.fpc_record_from_fen(14, b"R-0,0,0,0-1,1,1-1,1,1,1-0,0,0,0-0-x", 0, out.ctypes.data) == _lib.FPC_ERR_ARG
+    assert L.fpc_record_from_fen(14, b"R-0,0,0,0-1,1,1,1-1,1,1,1-0,0,0,0-0-rZ", 0, out.ctypes.data) == _lib.FPC_ERR_ARG
