@@ -107,7 +107,8 @@ class BatchedEnv:
 
     def observe(self, planes: bool = True, mask: bool = True, moves: bool = False, flat: bool = False,
                 k: int | torch.Tensor = -1, async_dense: bool = False, incremental: bool = False):
-        """Legal moves / result / planes / mask of every game (one fused kernel launch)."""
+        """Legal moves / result / planes / mask of every game: rules_kernel, plus expand_kernel for the dense tensors
+        (async_dense: do not wait for it, see join(); incremental: update the resident tensors in place)."""
         incremental = incremental and (planes, mask) in self._dense_known  # fresh buffers: full rewrite first
         self._dense_known.add((planes, mask))
         with torch.cuda.device(self.device):

@@ -15,8 +15,11 @@ the rules of step t+1 (FPC_FLAG_ASYNC_DENSE); the timed region ends after fpc_jo
          ids / plies come from pinned HOST memory every step and go back to it; planes and masks
          stay on the device exactly as the reference's GetEncodedStates(device="cuda") leaves them.
 
-`--impl reference` times the UNMODIFIED reference rules engine (oracle/_ref) on the host cores over
-the same workload (n slots resident as chess::Board objects, one ply per slot per step).
+`--impl reference` times the UNMODIFIED reference on the host cores over the same workload: `value` is its
+full path (rules engine + GetEncodedStates + legal mask through its own pybind module, oracle/_ref/binding_R14,
+one process per core); `engine_only` is its rules engine alone (oracle/_ref/libref_engine_R14.so, C++ threads).
+Extra objects on our line: roofline (expand_kernel timed per launch on its stream), rules_only, incremental_dense
+(resident tensors updated in place -- NOT the headline), perft (configs[0]), mcts (configs[3] sample), cpu_baseline.
 """
 from __future__ import annotations
 
