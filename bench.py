@@ -70,6 +70,7 @@ class ClockSampler:
         self.sm, self.reasons, self.smax = [], 0, None
         self.stop_flag = threading.Event()
         self.thread = None
+        self.poll_once = lambda: None
 
     def start(self):
         try:
@@ -85,13 +86,18 @@ class ClockSampler:
             get_reasons = (getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None)
                            or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons)
 
+            def once():
+                try:
+                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.reasons |= int(get_reasons(h))
+                except Exception:
+                    pass
+
+            self.poll_once = once  # the main thread also samples at fixed points inside the timed region
+
             def poll():
                 while not self.stop_flag.is_set():
-                    try:
-                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                        self.reasons |= int(get_reasons(h))
-                    except Exception:
-                        pass
+                    once()
                     time.sleep(0.002)
 
             self.thread = threading.Thread(target=poll, daemon=True)
@@ -272,6 +278,8 @@ def run_ours(args) -> None:
     e0.record()
     for _ in range(args.steps):
         step()
+    if rank == 0:
+        sampler.poll_once()  # the host runs ahead of the device: the queue is still full, a sample under load
     env.join()  # the main stream waits for the last expansion: every step's tensors are complete
     e1.record()
     barrier()
