@@ -82,6 +82,40 @@ def test_whole_trees_match_the_oracle(name, R, n_games, sims, batch_rotation):
     print(f"{name} rot={batch_rotation}: {len(trees)} games, {int(n_nodes.sum())} nodes, {n_dropped} dropped roots")
 
 
+def test_promotion_moves_collapse_into_one_child():
+    """the four promotion moves share one (plane, from) index, so they become ONE child, made with an
+    index-built move that does not promote.  Hand-made 14x14 position: a red pawn one step from its promotion row."""
+    R = 14
+    g = GEOMETRIES[R]
+    o = oracle_for(R)
+    rec = g.empty_record()
+    def put(r, c, color, ptype):
+        rec[r * R + c] = 0x80 | (color << 5) | (ptype << 2)
+        if ptype == 5:
+            rec[g.off_king + color] = r * R + c
+    put(13, 7, 0, 5), put(7, 0, 1, 5), put(0, 6, 2, 5), put(6, 13, 3, 5)   # kings
+    put(R // 4 + 1, 5, 0, 0)                                                # red pawn, promotion row is R/4
+    put(R // 4, 6, 1, 3)                                                    # a blue rook it can capture with promotion
+    legal = o.legal_moves(rec)
+    promos = [m for m in legal if ((int(m) >> 24) & 0xff) != 6]
+    assert len(promos) == 8  # push and capture, four promotion pieces each
+    roots = np.stack([rec] * 3)
+    trees = oracle_search(o, FakeNet(R), roots, 3, 20, batch_rotation=False)
+    m = run_gpu(R, roots, 20, batch_rotation=False)
+    flat, visits, prior, cnt = (t.cpu().numpy() for t in m.root_children())
+    n_distinct = len(set(o.move_flat_index(mv) for mv in legal))
+    assert n_distinct == len(legal) - 6
+    for gi, t in enumerate(trees):
+        ch = t.children[0]
+        assert cnt[gi] == len(ch) == n_distinct
+        assert flat[gi, : len(ch)].tolist() == [t.move_flat[c] for c in ch]
+        assert visits[gi, : len(ch)].tolist() == [t.visits[c] for c in ch]
+    # the child reached through the promotion index still holds a PAWN on the promotion row (index-built make)
+    push = o.move_flat_index(promos[0])
+    child = o.make_index(rec, push)
+    assert (child[(R // 4) * R + 5] >> 2) & 7 == 0
+
+
 def test_action_probs_and_capacity_errors():
     R = 8
     roots = np.stack([start_record("EIGHT_SIMPLE")] * 4)
