@@ -111,6 +111,41 @@ def test_make_full_and_index_match_oracle(name):
         assert np.array_equal(got[i], o.make_index(parents[i], idx[i])), i
 
 
+def test_hand_made_castling_cases():
+    """Castling details (engine/board.cpp:343-465) on hand-made 14x14 positions: legal lists, flags and the boards
+    after every legal move (rook relocation, rights update) against the oracle."""
+    from tests.util import castling_positions
+    R = 14
+    L = _lib.lib()
+    o = oracle_for(R)
+    recs = castling_positions(R)
+    n = len(recs)
+    env = BatchedEnv(R, n)
+    env.load(recs)
+    env.observe(planes=True, mask=True, moves=True)
+    torch.cuda.synchronize()
+    counts = env.counts.cpu().numpy()
+    moves = env.moves_buffer().cpu().numpy().view(np.uint64)
+    parents, mvs, castles = [], [], 0
+    for i in range(n):
+        want = o.legal_moves(recs[i])
+        assert counts[i] == len(want) and (moves[i, : len(want)] == want).all(), i
+        for m in want:
+            parents.append(recs[i])
+            mvs.append(m)
+            castles += ((int(m) >> 32) & 0xff) != R * R
+    assert castles >= 16
+    assert np.array_equal(env.mask_buffer().cpu().numpy(), o.mask(recs))
+    d_par = torch.as_tensor(np.stack(parents)).cuda()
+    d_mv = torch.as_tensor(np.array(mvs, dtype=np.uint64).view(np.int64)).cuda()
+    out, err = torch.empty_like(d_par), torch.zeros(len(mvs), dtype=torch.int32, device="cuda")
+    _lib.check(L.fpc_make_moves(R, d_par.data_ptr(), d_mv.data_ptr(), len(mvs), out.data_ptr(), err.data_ptr(), None))
+    got = out.cpu().numpy()
+    assert not err.any()
+    for i in range(len(mvs)):
+        assert np.array_equal(got[i], o.make_move(parents[i], mvs[i])), i
+
+
 def test_make_missing_piece_reports_error():
     R = 14
     g = GEOMETRIES[R]

@@ -103,3 +103,20 @@ def test_move_index_map(R):
         assert ref.move_flat_index(m) == o.move_flat_index(m)
     for a, b, c in [(0, 0, 0), (SEED, 5, 9), (2**63, 2**40, 2047)]:
         assert ref.mix(a, b, c) == o.mix(a, b, c)
+
+
+def test_hand_made_castling_cases():
+    """Castling details on the 14x14 board, oracle vs the unmodified engine: sets of pseudo and legal moves, and
+    the boards after every legal move (rook relocation, rights update)."""
+    from tests.util import castling_positions
+    ref, o = ref_for(14), oracle_for(14)
+    recs = castling_positions(14)
+    n_castles = 0
+    for rec in recs:
+        assert sorted(int(m) for m in ref.pseudo_moves(rec)) == sorted(int(m) for m in o.pseudo_moves(rec))
+        legal = [int(m) for m in o.legal_moves(rec)]
+        assert legal == sort_canonical(o, ref.legal_moves(rec))
+        for m in legal:
+            assert np.array_equal(ref.make_move(rec, m), o.make_move(rec, m))
+            n_castles += ((m >> 32) & 0xff) != 196
+    assert n_castles >= 16  # every colour castles both ways in several of the cases

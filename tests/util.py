@@ -50,3 +50,51 @@ def mixed_positions(name: str, n_positions: int, max_plies: int = 400):
 def oracle_legal_lists(R: int, recs: np.ndarray):
     o = oracle_for(R)
     return [o.legal_moves(r) for r in recs]
+
+
+def castling_positions(R: int = 14):
+    """Hand-made castling cases on the 14x14 board (engine/board.cpp:343-465), every colour to move: clean
+    castling both sides, a piece in between, the king in check, the crossed square attacked, the destination
+    attacked (pseudo-legal, rejected by the legal filter), the partner's rook on the rook square, rights off."""
+    g = GEOMETRIES[R]
+    base = start_record("STANDARD", castling=True)
+    out = []
+    for color in range(4):
+        rec = base.copy()
+        rec[g.off_turn] = color
+        # strip every knight, bishop, queen and pawn: kings and rooks only
+        for sq in range(g.nsq):
+            p = int(rec[sq])
+            if p & 0x80 and ((p >> 2) & 7) not in (3, 5):
+                rec[sq] = 0x18
+        out.append(rec.copy())                                   # clean: both castles available
+        ksq = int(rec[g.off_king + color])
+        kr, kc = divmod(ksq, R)
+        # unit step along the back rank towards the kingside rook
+        step = {0: (0, 1), 1: (1, 0), 2: (0, -1), 3: (-1, 0)}[color]
+        inward = {0: (-1, 0), 1: (0, 1), 2: (1, 0), 3: (0, -1)}[color]  # away from the own edge
+
+        def sq_at(k, depth=0):
+            return (kr + step[0] * k + inward[0] * depth) * R + (kc + step[1] * k + inward[1] * depth)
+
+        enemy_rook = 0x80 | (((color + 1) & 3) << 5) | (3 << 2)
+        partner_rook = 0x80 | (((color + 2) & 3) << 5) | (3 << 2)
+        for k in (1, 2, -1, -2, -3):                               # a blocker on each between square
+            r2 = rec.copy()
+            r2[sq_at(k)] = 0x80 | (color << 5) | (1 << 2)
+            out.append(r2)
+        for k in (0, 1, 2, -1, -2):                                # an enemy rook staring down the file at from / crossed / dest
+            r2 = rec.copy()
+            r2[sq_at(k, 5)] = enemy_rook
+            out.append(r2)
+        r2 = rec.copy()                                            # partner's rook on the kingside rook square
+        r2[sq_at(3)] = partner_rook
+        out.append(r2)
+        r2 = rec.copy()                                            # enemy rook there instead
+        r2[sq_at(3)] = enemy_rook
+        out.append(r2)
+        for bits in (0x80, 0x80 | 0x40, 0x80 | 0x20):              # rights: none, kingside only, queenside only
+            r2 = rec.copy()
+            r2[g.off_rights + color] = bits
+            out.append(r2)
+    return np.stack(out)
