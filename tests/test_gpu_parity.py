@@ -111,6 +111,55 @@ def test_make_full_and_index_match_oracle(name):
         assert np.array_equal(got[i], o.make_index(parents[i], idx[i])), i
 
 
+@pytest.mark.parametrize("R,n", [(14, 3000), (13, 1000), (10, 1000), (8, 1500)])
+def test_random_positions(R, n):
+    """Random, mostly unreachable positions (tests/util.random_positions; the oracle is pinned on the same generator
+    against the unmodified engine in tests/test_oracle_vs_ref.py): legal lists, results and flags, planes, masks,
+    and the board after the first and last legal move (full and index-built)."""
+    from tests.util import random_positions
+    g = GEOMETRIES[R]
+    L = _lib.lib()
+    o = oracle_for(R)
+    recs = random_positions(R, n, seed=11)
+    env = BatchedEnv(R, n)
+    env.load(recs)
+    env.observe(planes=True, mask=True, moves=True, flat=True)
+    torch.cuda.synchronize()
+    counts, status = env.counts.cpu().numpy(), env.status.cpu().numpy()
+    moves = env.moves_buffer().cpu().numpy().view(np.uint64)
+    flat = env.flat_buffer().cpu().numpy()
+    parents, mvs, idx = [], [], []
+    n_king_takers = 0
+    for i in range(n):
+        want = o.legal_moves(recs[i])
+        assert counts[i] == len(want) and (moves[i, : len(want)] == want).all(), i
+        res, nl, kc = o.game_result(recs[i])
+        assert (status[i] & 3) == res and bool(status[i] & _lib.STATUS_CAN_TAKE_KING) == kc, i
+        n_king_takers += kc
+        for m in ([want[0], want[-1]] if len(want) else []):
+            parents.append(recs[i])
+            mvs.append(m)
+            idx.append(o.move_flat_index(m))
+    assert n_king_takers > 0  # positions where a king can be captured do occur in this set
+    turns = recs[:, g.off_turn].astype(np.int32)
+    assert np.array_equal(env.planes_buffer().cpu().numpy(), o.encode(recs, turns))
+    assert np.array_equal(env.mask_buffer().cpu().numpy(), o.mask(recs))
+    d_par = torch.as_tensor(np.stack(parents)).cuda()
+    d_mv = torch.as_tensor(np.array(mvs, dtype=np.uint64).view(np.int64)).cuda()
+    d_ix = torch.as_tensor(np.array(idx, dtype=np.int32)).cuda()
+    out, err = torch.empty_like(d_par), torch.zeros(len(mvs), dtype=torch.int32, device="cuda")
+    _lib.check(L.fpc_make_moves(R, d_par.data_ptr(), d_mv.data_ptr(), len(mvs), out.data_ptr(), err.data_ptr(), None))
+    got = out.cpu().numpy()
+    assert not err.any()
+    for i in range(len(mvs)):
+        assert np.array_equal(got[i], o.make_move(parents[i], mvs[i])), i
+    _lib.check(L.fpc_make_index(R, d_par.data_ptr(), d_ix.data_ptr(), len(mvs), out.data_ptr(), err.data_ptr(), None))
+    got = out.cpu().numpy()
+    assert not err.any()
+    for i in range(len(mvs)):
+        assert np.array_equal(got[i], o.make_index(parents[i], idx[i])), i
+
+
 def test_hand_made_castling_cases():
     """Castling details (engine/board.cpp:343-465) on hand-made 14x14 positions: legal lists, flags and the boards
     after every legal move (rook relocation, rights update) against the oracle."""

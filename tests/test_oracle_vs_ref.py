@@ -120,3 +120,28 @@ def test_hand_made_castling_cases():
             assert np.array_equal(ref.make_move(rec, m), o.make_move(rec, m))
             n_castles += ((m >> 32) & 0xff) != 196
     assert n_castles >= 16  # every colour castles both ways in several of the cases
+
+
+@pytest.mark.parametrize("R", [14, 13, 10, 8])
+def test_random_positions(R):
+    """Random, mostly unreachable positions (tests/util.random_positions): pseudo and legal sets, the canonical
+    result, check tests and the board after every legal move, oracle vs the unmodified engine."""
+    from tests.util import random_positions
+    ref, o = ref_for(R), oracle_for(R)
+    early = 0
+    for rec in random_positions(R, 250):
+        assert sorted(int(m) for m in ref.pseudo_moves(rec)) == sorted(int(m) for m in o.pseudo_moves(rec))
+        legal = [int(m) for m in o.legal_moves(rec)]
+        assert legal == sort_canonical(o, ref.legal_moves(rec))
+        res, nl, kc = o.game_result(rec)
+        rr = ref.game_result(rec)
+        if rr != res:
+            assert res == 0 and kc and nl > 0
+            early += 1
+        for color in range(4):
+            assert ref.king_in_check(rec, color) == o.king_in_check(rec, color)
+        for m in legal[::3]:
+            assert np.array_equal(ref.make_move(rec, m), o.make_move(rec, m))
+            fi = o.move_flat_index(m)
+            assert np.array_equal(ref.make_index(rec, fi), o.make_index(rec, fi))
+    print(f"R={R}: GetGameResult early-out cases = {early}")

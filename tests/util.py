@@ -98,3 +98,35 @@ def castling_positions(R: int = 14):
             r2[g.off_rights + color] = bits
             out.append(r2)
     return np.stack(out)
+
+
+def random_positions(R: int, n: int, seed: int = 7):
+    """Random (mostly unreachable) positions: all four kings (one of them missing now and then), up to 10 random
+    pieces per colour on random on-board squares, pawns only on squares before their promotion line, random side to
+    move and random castling rights.  A differential test bed that does not depend on what playouts reach."""
+    g = GEOMETRIES[R]
+    rng = np.random.default_rng(seed)
+    squares = [sq for sq in range(g.nsq) if g.is_legal_location(sq // R, sq % R)]
+    out = []
+
+    def pawn_ok(color, r, c):  # strictly before the promotion line, in the pawn's direction of travel
+        return {0: r > R // 4, 2: r < 3 * R // 4, 1: c < 3 * R // 4, 3: c > R // 4}[color]
+
+    for _ in range(n):
+        rec = g.empty_record()
+        rec[g.off_turn] = rng.integers(0, 4)
+        free = list(rng.permutation(squares))
+        for color in range(4):
+            if rng.random() > 0.1:
+                sq = int(free.pop())
+                rec[sq] = 0x80 | (color << 5) | (5 << 2)
+                rec[g.off_king + color] = sq
+            for _ in range(int(rng.integers(0, 11))):
+                ptype = int(rng.choice([0, 0, 0, 1, 2, 3, 4]))
+                sq = int(free.pop())
+                if ptype == 0 and not pawn_ok(color, sq // R, sq % R):
+                    ptype = 1
+                rec[sq] = 0x80 | (color << 5) | (ptype << 2)
+            rec[g.off_rights + color] = 0x80 | (int(rng.integers(0, 2)) << 6) | (int(rng.integers(0, 2)) << 5)
+        out.append(rec)
+    return np.stack(out)
