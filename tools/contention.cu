@@ -15,6 +15,18 @@ __global__ void __launch_bounds__(128) fill(float4 *out, unsigned long long n16)
     if (warp * 256 + j * 32 + lane < n16) __stcs(dst + j * 32 + lane, make_float4(0, 0, 0, 0));
 }
 
+// persistent variant: `gridDim.x` CTAs of `blockDim.x` threads stride over the 4 KB groups in address order
+__global__ void fill_persistent(float4 *out, unsigned long long n16) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const unsigned long long groups = (n16 + 255) / 256, stride = (unsigned long long)gridDim.x * wpb;
+  for (unsigned long long warp = (unsigned long long)blockIdx.x * wpb + (threadIdx.x >> 5); warp < groups; warp += stride) {
+    float4 *dst = out + warp * 256;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (warp * 256 + j * 32 + lane < n16) __stcs(dst + j * 32 + lane, make_float4(0, 0, 0, 0));
+  }
+}
+
 __global__ void __launch_bounds__(128) co(int mode, int iters, int *sink) {
   __shared__ uint8_t sm[21000];
   for (int i = threadIdx.x; i < 21000; i += 128) sm[i] = (uint8_t)(i * 7 + 1);
@@ -75,6 +87,36 @@ int main() {
     }
     printf("%-28s co alone ~30 us; together: co %6.1f us, fill %6.1f us (%.0f GB/s)\n", names[mode], mode ? cosum / reps * 1e3 : 0.0f,
            sum / reps * 1e3, bytes / (sum / reps * 1e-3) / 1e9);
+  }
+  // a persistent fill with few warps per SM keeps the SM's store queue short: what does the LDS chain see?
+  {
+    int iters = 30;
+    float co_ms = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+      cudaEventRecord(h0, hi); co<<<1024, 128, 0, hi>>>(3, iters, sink); cudaEventRecord(h1, hi);
+      cudaDeviceSynchronize(); cudaEventElapsedTime(&co_ms, h0, h1);
+      iters = (int)(iters * 0.030f / co_ms) + 1;
+    }
+    for (int wps : {2, 4, 8, 16, 32}) {
+      const int threads = wps >= 8 ? 256 : wps * 32, ctas = 148 * (wps * 32 / threads);
+      for (int with_co = 0; with_co < 2; ++with_co) {
+        float fill_ms = 0, sum = 0, cosum = 0;
+        const int reps = 20;
+        for (int r = 0; r < reps + 3; ++r) {
+          cudaDeviceSynchronize();
+          cudaEventRecord(go, lo);
+          cudaStreamWaitEvent(hi, go, 0);
+          if (with_co) { cudaEventRecord(h0, hi); co<<<1024, 128, 0, hi>>>(3, iters, sink); cudaEventRecord(h1, hi); }
+          cudaEventRecord(e0, lo); fill_persistent<<<ctas, threads, 0, lo>>>(buf, n16); cudaEventRecord(e1, lo);
+          cudaDeviceSynchronize();
+          cudaEventElapsedTime(&fill_ms, e0, e1);
+          if (with_co) cudaEventElapsedTime(&co_ms, h0, h1);
+          if (r >= 3) { sum += fill_ms; cosum += co_ms; }
+        }
+        printf("persistent fill %2d warps/SM %s: co %6.1f us, fill %6.1f us (%.0f GB/s)\n", wps, with_co ? "beside the LDS chain" : "alone               ",
+               with_co ? cosum / reps * 1e3 : 0.0f, sum / reps * 1e3, bytes / (sum / reps * 1e-3) / 1e9);
+      }
+    }
   }
   // the same co-kernels beside cudaMemsetAsync (does the driver's memset run on the SMs or on a copy engine?)
   for (int mode = 0; mode <= 4; mode += 3) {
