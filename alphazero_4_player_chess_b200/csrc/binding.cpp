@@ -586,6 +586,12 @@ PYBIND11_MODULE(alphazero_cpp, m) {
       .def("GetMemory", [](Board &b) { return b.GetMemory(); })
       .def("GetGameResult", &Board::GetGameResult, py::arg("opt_player") = py::none())
       .def("IsMoveLegal", [](Board &, const Move &) { return false; })  // src/cpp/board.cpp:70-92 always returns false
+      // UI-only queries of the reference (src/cpp/board.cpp:50-57,120-232; used by the pygame viewer only): bound so
+      // that the name resolves, but not provided by this build
+      .def("GetSimpleState", [](Board &) -> py::object { throw std::runtime_error("GetSimpleState: viewer-only query, not provided by the B200 build"); })
+      .def("GetAttackedSquaresPlayers", [](Board &) -> py::object { throw std::runtime_error("GetAttackedSquaresPlayers: viewer-only query, not provided by the B200 build"); })
+      .def("GetAttackedSquaresTeams", [](Board &) -> py::object { throw std::runtime_error("GetAttackedSquaresTeams: viewer-only query, not provided by the B200 build"); })
+      .def("IsAttackedByPlayer", [](Board &, const BoardLocation &, PlayerColor) -> bool { throw std::runtime_error("IsAttackedByPlayer: viewer-only query, not provided by the B200 build"); })
       .def("GetLegalMoves", &Board::GetLegalMoves).def("TakeAction", &Board::TakeAction).def("record", [](const Board &b) { return py::bytes((const char *)b.rec.data(), b.rec.size()); })
       .def_static("ParseActionspace", &Board::ParseActionspace)
       .def_static("IsLegalLocation", [](int r, int c) { return Board::IsLegalLocation(r, c); })

@@ -53,7 +53,8 @@ def test_module_surface(az):
                  "ParseActionspace", "GetLegalMovesIndices", "GetLegalMovesMask", "GetPieces", "GetTurn", "SetTurn",
                  "CalculateHeuristic", "GetRootNode", "SetRootNode", "GetRootState", "SetRootState", "AppendToMemory",
                  "GetMemory", "IsLegalLocation", "nRows", "nCols", "invalidArea", "GetOpponent", "GetOpponentValue",
-                 "ChangePerspective", "GetPieceAt", "GetBoardLocation", "IsMoveLegal"]:
+                 "ChangePerspective", "GetPieceAt", "GetBoardLocation", "IsMoveLegal", "GetSimpleState",
+                 "GetAttackedSquaresPlayers", "GetAttackedSquaresTeams", "IsAttackedByPlayer"]:
         assert hasattr(az.Board, name), name
     for name in ["ChooseLeaf", "SelectChild", "Backpropagate", "BackpropagateNodes", "ExpandNodes", "GetChildren",
                  "GetVisitCount", "SetVisitCount", "GetMoveMade", "GetState", "IsExpanded"]:
