@@ -415,9 +415,23 @@ def run_ours(args) -> None:
             out["cpu_baseline"] = cpu_baseline_leg()
         if world == 1 and not args.no_mcts:
             out["perft"] = perft_leg(local)
-            del env
-            torch.cuda.empty_cache()
-            out["mcts"] = mcts_leg(rank, world, local)
+    # configs[3] / configs[4]: batched PUCT search, every rank on its own shard of games (no cross-GPU traffic in the
+    # search; one all_reduce of the per-rank rates for the report)
+    mcts = None
+    if not args.no_mcts:
+        del env
+        torch.cuda.empty_cache()
+        mcts = mcts_leg(rank, world, local)
+        if world > 1:
+            t = torch.tensor([mcts["value"], mcts["tree_kernels_only"]["value"], float(mcts["nodes"])], dtype=torch.float64,
+                             device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            mcts["value"], mcts["tree_kernels_only"]["value"], mcts["nodes"] = float(t[0]), float(t[1]), int(t[2])
+            mcts["games"] = mcts["games"] * world
+            mcts["note"] = f"sum over {world} ranks, each searching its own {mcts['games'] // world} games"
+    if rank == 0:
+        if mcts is not None:
+            out["mcts"] = mcts
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
