@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libfpc.so")
 FPC_MAX_MOVES = 300
 FPC_OK, FPC_ERR_ARG, FPC_ERR_CUDA, FPC_ERR_MOVE, FPC_ERR_OVERFLOW = 0, -1, -2, -3, -4
 STATUS_RESULT_MASK, STATUS_IN_CHECK, STATUS_CAN_TAKE_KING = 0x3, 0x100, 0x200
-STATUS_OVERFLOW, STATUS_FINISHED = 0x400, 0x800
+STATUS_OVERFLOW, STATUS_FINISHED, STATUS_CHECK = 0x400, 0x800, 0x1000
 FLAG_ASYNC_DENSE = 1
 FLAG_INCREMENTAL = 2
 

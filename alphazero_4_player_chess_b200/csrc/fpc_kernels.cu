@@ -10,7 +10,7 @@
 #include <vector>
 
 #include "../../include/fpc.h"
-#include "fpc_device.cuh"
+#include "fpc_rules.cuh"
 
 namespace fpc {
 
@@ -20,47 +20,17 @@ int cuda_check(cudaError_t e, const char *what);
 constexpr int WARPS_PER_BLOCK = 4;  // one warp per game
 constexpr int BLOCK_THREADS = WARPS_PER_BLOCK * 32;
 
-struct ObserveParams {
-  const uint8_t *boards_in;  // [n][REC]
-  uint8_t *boards_out;       // playout: updated records (may alias boards_in)
-  int n;
-  int need_movegen;
-  uint64_t *moves;      // [n][MAX_MOVES] or null
-  int32_t *flat;        // [n][MAX_MOVES] or null
-  int32_t *counts;      // [n] or null
-  int32_t *status;      // [n] or null
-  uint32_t *plane_bits; // [n][PLANE_WORDS] or null: input planes, 1 bit per cell
-  const int32_t *k;     // [n] or null
-  int k_all;            // -1: own turn
-  uint32_t *mask_bits;  // [n][MASK_WORDS] or null: legal-move mask, 1 bit per action
-  // Record of the ones a dense call leaves in the caller's tensors: [n][LIST_STRIDE] u16 (in: what the tensors
-  // hold now, out: what they hold after this call).  With inc_planes / inc_mask set the tensors are updated in
-  // place -- previous ones cleared, current ones set -- instead of being rewritten (FPC_FLAG_INCREMENTAL).
-  uint16_t *lists;
-  int list_cells, list_flats;  // which halves of the record this call maintains (planes / mask requested)
-  float *inc_planes, *inc_mask;
-  // playout
-  int playout;
-  uint64_t seed;
-  uint64_t *game;
-  int32_t *ply;
-  const uint8_t *start;
-  int max_plies;
-  uint64_t game_stride;
-  uint64_t *chosen;
-  unsigned long long *counters;
-};
-
 // Dense outputs.  The reference tensors are dense f32 ([n,24,R,R] planes, [n,8R+8,R,R] mask) holding
 // ~40 and ~19 ones per game among 4,704 and 23,520 cells; writing them is the HBM-bound part of the
 // path (113 KB per game at 14x14).  rules_kernel produces them as bit sets (1 bit per cell, 3.5 KB
-// per game); expand_kernel streams the bits out as f32.  The two kernels run on different streams so
-// that the expansion of one batch overlaps the integer work of the next (FPC_FLAG_ASYNC_DENSE,
-// fpc_join).
+// per game, zero-filled and set straight in global memory = L2); expand_kernel streams the bits out as f32.
+// The two kernels run on different streams so that the expansion of one batch overlaps the integer work
+// of the next (FPC_FLAG_ASYNC_DENSE, fpc_join).
 
-// List of one game (u16 units): [0] number of mask entries, [1] number of plane entries, [2, 66) plane cell
-// indices ch*R*R + row*R + col (already rotated), [66, 366) flat action indices; 368 u16 = 736 B.
-constexpr int LIST_PLANES = 2, LIST_FLAT = 66, LIST_STRIDE = 368;
+static_assert(STATUS_IN_CHECK == FPC_STATUS_IN_CHECK && STATUS_CAN_TAKE_KING == FPC_STATUS_CAN_TAKE_KING &&
+                  STATUS_OVERFLOW == FPC_STATUS_OVERFLOW && STATUS_FINISHED == FPC_STATUS_FINISHED &&
+                  STATUS_CHECK == FPC_STATUS_CHECK,
+              "status bits of fpc_rules.cuh and include/fpc.h");
 
 #define CK(expr)                                   \
   do {                                             \
@@ -68,346 +38,15 @@ constexpr int LIST_PLANES = 2, LIST_FLAT = 66, LIST_STRIDE = 368;
     if (rc_ != FPC_OK) return rc_;                 \
   } while (0)
 
-// Record <-> mailbox without per-byte index arithmetic: lane l < 2R owns half a row (row l/2, columns
-// (l&1)*H .. +H, H = ceil(R/2)), so row / column / legality are lane constants and the column loop unrolls.
+// The rules kernel: one warp per game (fpc_rules.cuh).  Legal moves, result, the bit sets of the dense outputs,
+// and (playout) the move choice and make-move.  It touches only the board store and compact per-game outputs.
 template <class G>
-struct HalfRow {
-  static constexpr int H = (G::R + 1) / 2;
-  int row, c0;
-  bool active, corner_row;
-  __device__ __forceinline__ explicit HalfRow(int lane)
-      : row(lane >> 1), c0((lane & 1) * H), active(lane < 2 * G::R),
-        corner_row((lane >> 1) < G::IA || (lane >> 1) > G::R - 1 - G::IA) {}
-  // is column c0 + j an on-board square of this lane's row?
-  __device__ __forceinline__ bool on_board(int j) const {
-    const int c = c0 + j;
-    return active && c < G::R && !(corner_row && (c < G::IA || c > G::R - 1 - G::IA));
-  }
-};
-
-template <class G>
-__device__ __forceinline__ void load_record(WarpScratch<G> &s, const uint8_t *rec_g, int lane) {
-  // mailbox <- WALL; record -> staging (coalesced 16-byte loads: the record is contiguous)
-  reinterpret_cast<uint4 *>(s.mb)[lane] = make_uint4(0x1C1C1C1Cu, 0x1C1C1C1Cu, 0x1C1C1C1Cu, 0x1C1C1C1Cu);
-  reinterpret_cast<uint4 *>(s.mb)[lane + 32] = make_uint4(0x1C1C1C1Cu, 0x1C1C1C1Cu, 0x1C1C1C1Cu, 0x1C1C1C1Cu);
-  if (lane < G::REC / 16)
-    reinterpret_cast<uint4 *>(s.rec)[lane] = reinterpret_cast<const uint4 *>(rec_g)[lane];  // may be updated in place: no __ldg
-  if (lane < 4) s.king[lane] = NO_SQ;
-  __syncwarp();
-  if (lane < 4) s.rights[lane] = s.rec[G::OFF_RIGHTS + lane];
-  if (lane == 0) s.turn = s.rec[G::OFF_TURN] & 3;
-}
-
-template <class G>
-__device__ __forceinline__ void store_record(WarpScratch<G> &s, uint8_t *rec_g, int lane) {
-  const HalfRow<G> hr(lane);
-#pragma unroll
-  for (int j = 0; j < HalfRow<G>::H; ++j) {
-    const int c = hr.c0 + j;
-    if (hr.active && c < G::R) s.rec[hr.row * G::R + c] = hr.on_board(j) ? s.mb[G::mb(hr.row, c)] : (uint8_t)EMPTY;
-  }
-  if (lane < G::REC - G::NSQ) {
-    const int i = G::NSQ + lane;
-    uint32_t v = 0;
-    if (i == G::OFF_TURN) {
-      v = s.turn;
-    } else if (i < G::OFF_KING) {
-      v = s.rights[i - G::OFF_RIGHTS];
-    } else if (i < G::OFF_KING + 4) {
-      const int k = s.king[i - G::OFF_KING];
-      v = k == NO_SQ ? G::NSQ : G::sq_of_mb(k);
-    }
-    s.rec[i] = (uint8_t)v;
-  }
-  __syncwarp();
-  if (lane < G::REC / 16) reinterpret_cast<uint4 *>(rec_g)[lane] = reinterpret_cast<const uint4 *>(s.rec)[lane];
-}
-
-// The rules kernel: one warp per game.  Legal moves, result, the bit sets of the dense outputs,
-// and (playout) the move choice and make-move.  It touches only the board store and compact
-// per-game outputs.
-template <class G>
-__global__ void __launch_bounds__(BLOCK_THREADS, 10) rules_kernel(const __grid_constant__ ObserveParams P) {
-  __shared__ WarpScratch<G> scratch[WARPS_PER_BLOCK];
+__global__ void __launch_bounds__(BLOCK_THREADS) rules_kernel(const __grid_constant__ ObserveParams P) {
+  __shared__ RulesScratch<G> scratch[WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * WARPS_PER_BLOCK + wib;
   if (g >= P.n) return;
-  WarpScratch<G> &s = scratch[wib];
-  const unsigned lt_mask = (1u << lane) - 1u;
-
-  if (P.mask_bits)
-    for (int i = lane; i < G::MASK_STRIDE / 4; i += 32) reinterpret_cast<uint4 *>(s.mask_bits)[i] = make_uint4(0, 0, 0, 0);
-  if (P.plane_bits)
-    for (int i = lane; i < G::PLANE_STRIDE / 4; i += 32) reinterpret_cast<uint4 *>(s.plane_bits)[i] = make_uint4(0, 0, 0, 0);
-  // playout bookkeeping is read up front: with zero-copy host buffers each load is a PCIe round trip
-  const uint64_t game_id = P.playout ? P.game[g] : 0;
-  const int ply = P.playout ? P.ply[g] : 0;
-  load_record<G>(s, P.boards_in + (size_t)g * G::REC, lane);
-  __syncwarp();
-  const int turn = s.turn;
-
-  // ---- unpack into the mailbox + piece scan: king squares, the mover's piece list, the
-  //      input-plane bits (src/cpp/board.cpp:318-344) ------------------------------------------
-  const bool want_planes = P.plane_bits || (P.lists && P.list_cells);
-  int rot = 0;
-  if (want_planes) {
-    rot = P.k ? P.k[g] : (P.k_all < 0 ? turn : P.k_all);
-    rot &= 3;
-  }
-  int np = 0, n_cells = 0;
-  {
-    const HalfRow<G> hr(lane);
-#pragma unroll
-    for (int j = 0; j < HalfRow<G>::H; ++j) {
-      const int r = hr.row, c = hr.c0 + j;
-      uint32_t p = EMPTY;
-      if (hr.on_board(j)) {
-        p = s.rec[r * G::R + c];
-        if (!present(p)) p = EMPTY;  // one canonical empty byte: the line scans test bits 7 and 2
-        put_cell(s.mb, G::mb(r, c), p);
-        if (present(p) && type_of(p) == KING) s.king[color_of(p)] = (uint8_t)G::mb(r, c);
-      }
-      const bool mine = present(p) && color_of(p) == turn;
-      const unsigned b = __ballot_sync(FULL, mine);
-      if (mine) {
-        const int idx = np + __popc(b & lt_mask);
-        if (idx < 64) s.plist[idx] = (uint8_t)G::mb(r, c);
-      }
-      np += __popc(b);
-      if (want_planes) {
-        const unsigned pb = __ballot_sync(FULL, present(p));
-        if (present(p)) {
-          // ch = ((color - turn) mod 4)*6 + type - 1, -1 wrapping to 23 (src/cpp/board.cpp:336)
-          int ch = ((color_of(p) - turn) & 3) * 6 + type_of(p) - 1;
-          if (ch < 0) ch += 24;
-          // torch.rot90(k) on the last two dims: one quarter turn sends (r,c) -> (R-1-c, r)
-          const int rr = rot == 0 ? r : (rot == 1 ? G::R - 1 - c : (rot == 2 ? G::R - 1 - r : c));
-          const int cc = rot == 0 ? c : (rot == 1 ? r : (rot == 2 ? G::R - 1 - c : G::R - 1 - r));
-          const int bit = ch * G::NSQ + rr * G::R + cc;
-          if (P.plane_bits) atomicOr(&s.plane_bits[bit >> 5], 1u << (bit & 31));
-          const int idx = n_cells + __popc(pb & lt_mask);
-          if (idx < 64) s.list[LIST_PLANES + idx] = (uint16_t)bit;
-        }
-        n_cells += __popc(pb);
-      }
-    }
-  }
-  if (np > 64) np = 64;
-  if (n_cells > 64) n_cells = 64;
-  __syncwarp();
-
-  int n_legal = 0, status = 0;
-  uint32_t chosen_mv = 0;
-  if (P.need_movegen) {
-    const int king_sq = s.king[turn];
-    // ---- pseudo-legal generation (engine/board.cpp:846-889); nothing without a king ------
-    int n_pseudo = 0;
-    bool overflow = false;
-    if (king_sq != NO_SQ) {
-      const int items = np * 4;  // (piece, line): two runs of moves each
-      for (int base = 0; base < items; base += 32) {
-        const int item = base + lane;
-        Run lo{0, 0, 0}, hi{0, 0, 0};
-        int kind = 0, from = 0;
-        if (item < items) {
-          from = s.plist[item >> 2];
-          gen_item<G>(s.mb, from, item & 3, lo, hi, kind);
-        }
-        const int cnt = lo.cnt + hi.cnt;  // <= 26: two rays of at most 13 squares
-        // exclusive prefix sum of cnt over the warp, bit-sliced over five ballots: votes and popcounts
-        // only, no trip through the shuffle / shared-memory pipe
-        int excl = 0, total = 0;
-#pragma unroll
-        for (int bit = 0; bit < 5; ++bit) {
-          const unsigned b = __ballot_sync(FULL, (cnt >> bit) & 1);
-          excl += __popc(b & lt_mask) << bit;
-          total += __popc(b) << bit;
-        }
-        int at = n_pseudo + excl;
-        if (n_pseudo + total > MAX_MOVES) {
-          overflow = true;
-        } else {
-          for (int j = 0; j < lo.cnt; ++j)
-            s.moves[at++] = kind == 0 ? pack_compact<G>(from, from + lo.delta * (j + 1), lo.plane0 + j, NO_PIECE, 0)
-                                      : pack_compact<G>(from, from + lo.delta, lo.plane0, KNIGHT + j, 0);
-          for (int j = 0; j < hi.cnt; ++j) s.moves[at++] = pack_compact<G>(from, from + hi.delta * (j + 1), hi.plane0 + j, NO_PIECE, 0);
-          n_pseudo += total;
-        }
-      }
-      // castling: two candidates, each needs two attack tests (engine/board.cpp:343-465)
-      {
-        uint32_t mv = 0;
-        if (lane < 2) mv = gen_castle<G>(s.mb, king_sq, turn, s.rights[turn], lane);
-        const unsigned b = __ballot_sync(FULL, mv != 0);
-        if (b) {
-          if (n_pseudo + __popc(b) > MAX_MOVES) {
-            overflow = true;
-          } else {
-            if (mv) s.moves[n_pseudo + __popc(b & lt_mask)] = mv;
-            n_pseudo += __popc(b);
-          }
-        }
-      }
-      __syncwarp();
-    }
-    // ---- legal filter (src/cpp/board.cpp:94-118), compacted in place -----------------------
-    bool takes_king = false;
-    for (int base = 0; base < n_pseudo; base += 32) {
-      const int i = base + lane;
-      uint32_t mv = 0;
-      bool ok = false;
-      if (i < n_pseudo) {
-        mv = s.moves[i];
-        ok = king_safe_after<G>(s.mb, s.king, turn, mv);
-        if (ok) {
-          const uint32_t cap = s.mb[mv & 0xff];
-          if (((mv >> 8) & 3) == 0 && present(cap) && type_of(cap) == KING) takes_king = true;
-        }
-      }
-      const unsigned b = __ballot_sync(FULL, ok);
-      __syncwarp();
-      if (ok) s.moves[n_legal + __popc(b & lt_mask)] = mv;
-      n_legal += __popc(b);
-    }
-    __syncwarp();
-    takes_king = __any_sync(FULL, takes_king);
-
-    // ---- result (engine/board.cpp:891-939, order-independent contract) ---------------------
-    const bool ry = (turn & 1) == 0;
-    int result = 0;
-    if (king_sq == NO_SQ) {
-      result = ry ? 2 : 1;
-    } else if (n_legal == 0) {
-      Patch none{0x1000, 0x1000, 0x1000, 0x1000, 0, 0};
-      const bool in_check = attacked_by_team<G, false>(s.mb, 1 - (turn & 1), king_sq, none);
-      result = in_check ? (ry ? 2 : 1) : 3;
-      if (in_check) status |= FPC_STATUS_IN_CHECK;
-    }
-    status |= result;
-    if (takes_king) status |= FPC_STATUS_CAN_TAKE_KING;
-    if (overflow) status |= FPC_STATUS_OVERFLOW;
-
-    // ---- canonical order: rank = number of smaller keys (keys are unique) ------------------
-    uint32_t pick = 0xffffffffu;
-    if (P.playout && result == 0)
-      pick = (uint32_t)(((mix64(P.seed, game_id, (uint64_t)ply) >> 32) * (uint64_t)n_legal) >> 32);
-    const bool want_lists = P.moves || P.flat;
-    const bool want_flats = P.lists && P.list_flats;
-    if (want_lists || P.mask_bits || P.playout || want_flats) {
-      // pad to a multiple of four with keys above every real one: the rank loop compares four keys per load
-      if (lane < 4) s.moves[n_legal + lane] = 0xffffffffu;
-      __syncwarp();
-      for (int base = 0; base < n_legal; base += 32) {
-        const int i = base + lane;
-        if (i < n_legal) {
-          const uint32_t mv = s.moves[i];
-          const uint32_t flat = mv >> 17;
-          if (P.mask_bits) atomicOr(&s.mask_bits[flat >> 5], 1u << (flat & 31));
-          if (want_flats) s.list[LIST_FLAT + i] = (uint16_t)flat;
-          if (want_lists || P.playout) {
-            int rank = 0;
-            for (int j = 0; j < n_legal; j += 4) {
-              const uint4 q = *reinterpret_cast<const uint4 *>(&s.moves[j]);
-              rank += (q.x < mv) + (q.y < mv) + (q.z < mv) + (q.w < mv);
-            }
-            if (P.moves) P.moves[(size_t)g * MAX_MOVES + rank] = expand_move<G>(s.mb, s.rights, mv);
-            if (P.flat) P.flat[(size_t)g * MAX_MOVES + rank] = (int32_t)flat;
-            if ((uint32_t)rank == pick) chosen_mv = mv;
-          }
-        }
-      }
-      __syncwarp();
-    }
-    if (lane == 0) {
-      if (P.counts) P.counts[g] = n_legal;
-    }
-  }
-
-  // ---- bit sets of the dense outputs (coalesced; expand_kernel turns them into f32) --------------
-  __syncwarp();
-  if (P.plane_bits)
-    for (int i = lane; i < G::PLANE_STRIDE / 4; i += 32)
-      reinterpret_cast<uint4 *>(P.plane_bits + (size_t)g * G::PLANE_STRIDE)[i] = reinterpret_cast<const uint4 *>(s.plane_bits)[i];
-  if (P.mask_bits)
-    for (int i = lane; i < G::MASK_STRIDE / 4; i += 32)
-      reinterpret_cast<uint4 *>(P.mask_bits + (size_t)g * G::MASK_STRIDE)[i] = reinterpret_cast<const uint4 *>(s.mask_bits)[i];
-
-  // ---- the record of ones / in-place update of the dense tensors (FPC_FLAG_INCREMENTAL) ---------
-  if (P.lists) {
-    uint16_t *gl = P.lists + (size_t)g * LIST_STRIDE;
-    const int new_flats = P.list_flats ? n_legal : 0, new_cells = P.list_cells ? n_cells : 0;
-    if (P.inc_planes || P.inc_mask) {
-      const int old_flats = gl[0], old_cells = gl[1];
-      if (P.inc_planes) {
-        float *dst = P.inc_planes + (size_t)g * G::SSZ;
-        for (int i = lane; i < old_cells; i += 32) dst[gl[LIST_PLANES + i]] = 0.0f;
-      }
-      if (P.inc_mask) {
-        float *dst = P.inc_mask + (size_t)g * G::ASZ;
-        for (int i = lane; i < old_flats; i += 32) dst[gl[LIST_FLAT + i]] = 0.0f;
-      }
-      __syncwarp();  // warp-level memory ordering: every clear precedes every set (a cell may be in both lists)
-      if (P.inc_planes) {
-        float *dst = P.inc_planes + (size_t)g * G::SSZ;
-        for (int i = lane; i < new_cells; i += 32) dst[s.list[LIST_PLANES + i]] = 1.0f;
-      }
-      if (P.inc_mask) {
-        float *dst = P.inc_mask + (size_t)g * G::ASZ;
-        for (int i = lane; i < new_flats; i += 32) dst[s.list[LIST_FLAT + i]] = 1.0f;
-      }
-    }
-    if (lane == 0) {
-      s.list[0] = (uint16_t)new_flats;
-      s.list[1] = (uint16_t)new_cells;
-    }
-    __syncwarp();
-    for (int i = lane; i < LIST_STRIDE / 8; i += 32) reinterpret_cast<uint4 *>(gl)[i] = reinterpret_cast<const uint4 *>(s.list)[i];
-  }
-
-  // ---- playout: play the chosen move or re-seed the slot ------------------------------------
-  if (P.playout) {
-    const unsigned who = __ballot_sync(FULL, chosen_mv != 0);
-    const int result = status & FPC_STATUS_RESULT_MASK;
-    uint64_t chosen64 = 0;
-    bool finished = false;
-    if (result == 0 && who) {
-      const uint32_t mv = __shfl_sync(FULL, chosen_mv, __ffs(who) - 1);
-      if (P.chosen) chosen64 = expand_move<G>(s.mb, s.rights, mv);
-      __syncwarp();
-      if (lane == 0) make_compact<G>(s, mv);
-      __syncwarp();
-      if (ply + 1 >= P.max_plies) finished = true;
-    } else {
-      finished = true;
-    }
-    if (finished) {
-      status |= FPC_STATUS_FINISHED;
-      if (lane < G::REC / 16)
-        reinterpret_cast<uint4 *>(P.boards_out + (size_t)g * G::REC)[lane] =
-            __ldg(reinterpret_cast<const uint4 *>(P.start) + lane);
-    } else {
-      store_record<G>(s, P.boards_out + (size_t)g * G::REC, lane);
-    }
-    if (lane == 0) {
-      if (P.chosen) P.chosen[g] = chosen64;
-      if (finished) {
-        P.game[g] = game_id + P.game_stride;
-        P.ply[g] = 0;
-      } else {
-        P.ply[g] = ply + 1;
-      }
-      if (P.counters) {
-        atomicAdd(&P.counters[0], 1ull);
-        atomicAdd(&P.counters[6], (unsigned long long)n_legal);
-        if (finished) {
-          atomicAdd(&P.counters[1], 1ull);
-          atomicAdd(&P.counters[2 + result], 1ull);
-        }
-        if (status & FPC_STATUS_OVERFLOW) atomicAdd(&P.counters[7], 1ull);
-      }
-    }
-  }
-  if (lane == 0 && P.status) P.status[g] = status;
+  rules_warp<G>(P, scratch[wib], g, lane);
 }
 
 // bits -> dense f32 (0.0 / 1.0).  One tensor per launch half: games x (words_per_game words ->

@@ -55,6 +55,7 @@ extern "C" {
 #define FPC_STATUS_CAN_TAKE_KING 0x200 /* some legal move captures a king */
 #define FPC_STATUS_OVERFLOW 0x400      /* move buffer overflow */
 #define FPC_STATUS_FINISHED 0x800      /* playout only: the game in this slot ended and was re-seeded */
+#define FPC_STATUS_CHECK 0x1000        /* side to move is in check (engine/board.cpp:941-960), legal moves or not */
 
 const char *fpc_last_error(void);
 int fpc_version(void);

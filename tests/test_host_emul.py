@@ -1,7 +1,8 @@
-"""CPU: the product's device rules header (csrc/fpc_device.cuh) compiled for the host and walked
-sequentially (tests/host_emul/emul.cpp), against the oracle.  This checks the rules code the kernels
-run -- generation, castling, legal filter, result, make, canonical order -- in the GPU-less build
-container; the warp choreography is covered by the -m gpu tests."""
+"""CPU: the product's rules kernel body (csrc/fpc_rules.cuh: rules_warp, the code every warp of rules_kernel runs)
+compiled for the host and run under a fibre-per-lane warp emulator (tests/host_emul/), against the oracle.  This
+checks the whole warp choreography -- line tables, pins, checks, generation, castling, canonical order, the bit sets
+of the dense outputs, the playout pick and make-move -- in the GPU-less build container; the -m gpu tests run the
+same code on a B200."""
 import ctypes as C
 import os
 import subprocess
@@ -10,52 +11,191 @@ import numpy as np
 import pytest
 
 from alphazero_4_player_chess_b200.fen import START_FENS, start_record
-from tests.util import SEED, oracle_for
+from alphazero_4_player_chess_b200.geometry import GEOMETRIES
+from tests.util import SEED, castling_positions, oracle_for
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
-_u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+CSRC = os.path.join(ROOT, "alphazero_4_player_chess_b200", "csrc")
+
+
+class Params(C.Structure):
+    """struct fpc::ObserveParams (csrc/fpc_rules.cuh)."""
+    _fields_ = [("boards_in", C.c_void_p), ("boards_out", C.c_void_p), ("n", C.c_int), ("need_movegen", C.c_int),
+                ("moves", C.c_void_p), ("flat", C.c_void_p), ("counts", C.c_void_p), ("status", C.c_void_p),
+                ("plane_bits", C.c_void_p), ("k", C.c_void_p), ("k_all", C.c_int), ("mask_bits", C.c_void_p),
+                ("lists", C.c_void_p), ("list_cells", C.c_int), ("list_flats", C.c_int), ("inc_planes", C.c_void_p),
+                ("inc_mask", C.c_void_p), ("playout", C.c_int), ("seed", C.c_uint64), ("game", C.c_void_p),
+                ("ply", C.c_void_p), ("start", C.c_void_p), ("max_plies", C.c_int), ("game_stride", C.c_uint64),
+                ("chosen", C.c_void_p), ("counters", C.c_void_p)]
 
 
 @pytest.fixture(scope="module")
 def emul():
     src = os.path.join(HERE, "host_emul", "emul.cpp")
-    hdr = os.path.join(ROOT, "alphazero_4_player_chess_b200", "csrc", "fpc_device.cuh")
+    deps = [src, os.path.join(HERE, "host_emul", "warp_emul.h"), os.path.join(CSRC, "fpc_device.cuh"),
+            os.path.join(CSRC, "fpc_rules.cuh")]
     so = os.path.join(HERE, "host_emul", "libemul.so")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-I/usr/local/cuda/include",
-                               "-I" + os.path.dirname(hdr), "-o", so, src])
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-DFPC_HOST_EMUL",
+                               "-I/usr/local/cuda/include", "-I" + CSRC, "-o", so, src])
     L = C.CDLL(so)
-    L.emul_step.argtypes = [C.c_int, _u8p, C.c_uint64, C.c_uint64, C.c_uint64, _u8p, _u64p, C.POINTER(C.c_int),
-                            C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    L.emul_rules.argtypes = [C.c_int, C.POINTER(Params)]
     return L
 
 
-@pytest.mark.parametrize("name,n_games,max_plies", [("STANDARD", 12, 500), ("THIRTEEN", 6, 300), ("TEN", 8, 300),
-                                                    ("EIGHT", 8, 300), ("EIGHT_SIMPLE", 8, 300)])
+class Harness:
+    """One batch of positions through rules_warp: every output the kernel can produce."""
+
+    def __init__(self, L, R):
+        self.L, self.R, self.g = L, R, GEOMETRIES[R]
+        ps, ms, ls = C.c_int(), C.c_int(), C.c_int()
+        assert L.emul_strides(R, C.byref(ps), C.byref(ms), C.byref(ls)) == 0
+        self.plane_stride, self.mask_stride, self.list_stride = ps.value, ms.value, ls.value
+
+    def observe(self, recs, k_all=-1, playout=None, dense=True):
+        """playout: None or dict(seed, games, plies, start, max_plies)."""
+        recs = np.ascontiguousarray(recs, dtype=np.uint8)
+        n = len(recs)
+        out = dict(moves=np.zeros((n, 300), np.uint64), flat=np.zeros((n, 300), np.int32), counts=np.zeros(n, np.int32),
+                   status=np.zeros(n, np.int32), plane_bits=np.full((n, self.plane_stride), 0xDEADBEEF, np.uint32),
+                   mask_bits=np.full((n, self.mask_stride), 0xDEADBEEF, np.uint32))
+        p = Params()
+        p.boards_in = recs.ctypes.data
+        p.n, p.need_movegen, p.k_all = n, 1, k_all
+        for name in ("moves", "flat", "counts", "status"):
+            setattr(p, name, out[name].ctypes.data)
+        if dense:
+            p.plane_bits, p.mask_bits = out["plane_bits"].ctypes.data, out["mask_bits"].ctypes.data
+        if playout is not None:
+            out["boards"] = recs.copy()
+            out["game"] = np.ascontiguousarray(playout["games"], dtype=np.uint64)
+            out["ply"] = np.ascontiguousarray(playout["plies"], dtype=np.int32)
+            out["chosen"] = np.zeros(n, np.uint64)
+            out["counters"] = np.zeros(8, np.uint64)
+            self._start = np.ascontiguousarray(playout["start"], dtype=np.uint8)
+            p.boards_out = out["boards"].ctypes.data
+            p.playout, p.seed, p.max_plies, p.game_stride = 1, playout["seed"], playout["max_plies"], 1000
+            p.game, p.ply, p.start = out["game"].ctypes.data, out["ply"].ctypes.data, self._start.ctypes.data
+            p.chosen, p.counters = out["chosen"].ctypes.data, out["counters"].ctypes.data
+        assert self.L.emul_rules(self.R, C.byref(p)) == 0
+        return out
+
+    def dense(self, bits, n_floats):
+        """bit set -> the 0/1 f32 tensor expand_kernel would write."""
+        b = np.unpackbits(np.ascontiguousarray(bits).view(np.uint8), axis=1, bitorder="little")
+        return b[:, :n_floats].astype(np.float32)
+
+
+def check_positions(h, o, recs, k_all=-1):
+    R, g = h.R, h.g
+    out = h.observe(recs, k_all=k_all)
+    n_check = 0
+    for i, rec in enumerate(recs):
+        want = o.legal_moves(rec)
+        nl = int(out["counts"][i])
+        assert nl == len(want), (i, nl, len(want))
+        assert np.array_equal(out["moves"][i, :nl], want), i
+        assert out["flat"][i, :nl].tolist() == [o.move_flat_index(m) for m in want]
+        res, _, kc = o.game_result(rec)
+        st = int(out["status"][i])
+        turn = int(rec[R * R])
+        has_king = any(int(b) == (0x80 | (turn << 5) | (5 << 2)) for b in rec[: R * R])
+        if res != 0 and has_king and nl > 0:
+            # the reference's order-dependent early-out (SURVEY 8a row 8): IN_PROGRESS + CAN_TAKE_KING here
+            assert (st & 3) == 0 and (st & 0x200)
+        else:
+            assert (st & 3) == res, (i, st, res)
+            assert bool(st & 0x200) == kc
+        in_check = has_king and o.king_in_check(rec, turn)
+        assert bool(st & 0x1000) == in_check, (i, st)
+        n_check += in_check
+    turns = recs[:, R * R].astype(np.int32)
+    k = turns if k_all < 0 else np.full(len(recs), k_all, np.int32)
+    planes = h.dense(out["plane_bits"], g.state_space_size).reshape(-1, 24, R, R)
+    assert np.array_equal(planes, o.encode(recs, k))
+    mask = h.dense(out["mask_bits"], g.action_space_size).reshape(-1, g.num_action_channels, R, R)
+    assert np.array_equal(mask, o.mask(recs))
+    # padding words of the bit sets are written (zero), not left as they were
+    assert not (out["plane_bits"][:, (g.state_space_size + 31) // 32:] != 0).any()
+    return n_check
+
+
+@pytest.mark.parametrize("name,n_games,max_plies", [("STANDARD", 10, 600), ("THIRTEEN", 5, 300), ("TEN", 6, 300),
+                                                    ("EIGHT", 6, 300), ("EIGHT_SIMPLE", 6, 300)])
 @pytest.mark.parametrize("castling", [True, False])
-def test_device_rules_on_host(emul, name, n_games, max_plies, castling):
+def test_rules_warp_on_playouts(emul, name, n_games, max_plies, castling):
     _, R = START_FENS[name]
     o = oracle_for(R)
+    h = Harness(emul, R)
     start = start_record(name, castling=castling)
     positions = 0
     for game in range(n_games):
         p = o.playout(start, SEED, game, max_plies)
-        for ply in range(p["n"]):
-            rec = np.ascontiguousarray(p["recs"][ply])
-            out = np.zeros_like(rec)
-            moves = np.zeros(300, dtype=np.uint64)
-            nl, st, npseudo, chosen = C.c_int(), C.c_int(), C.c_int(), C.c_uint64()
-            assert emul.emul_step(R, rec, SEED, game, ply, out, moves, C.byref(nl), C.byref(st), C.byref(chosen),
-                                  C.byref(npseudo)) == 0
-            want = o.legal_moves(rec)
-            assert nl.value == len(want) and np.array_equal(moves[: nl.value], want), (game, ply)
-            assert npseudo.value == len(o.pseudo_moves(rec))
-            res, _, kc = o.game_result(rec)
-            assert (st.value & 3) == res and bool(st.value & 0x200) == kc
-            assert chosen.value == int(p["moves"][ply])
-            if res == 0 and ply + 1 < p["n"]:
-                assert np.array_equal(out, p["recs"][ply + 1]), (game, ply)
-            positions += 1
+        recs = p["recs"]
+        n = p["n"]
+        check_positions(h, o, recs, k_all=-1 if game % 2 == 0 else game % 4)
+        # the playout step: pick, make-move, re-seeding, counters
+        out = h.observe(recs, playout=dict(seed=SEED, games=np.full(n, game), plies=np.arange(n), start=start,
+                                           max_plies=max_plies), dense=False)
+        for ply in range(n):
+            assert int(out["chosen"][ply]) == int(p["moves"][ply])
+            st = int(out["status"][ply])
+            if p["result"][ply] == 0 and ply + 1 < max_plies:
+                assert not st & 0x800
+                assert np.array_equal(out["boards"][ply], recs[ply + 1] if ply + 1 < n else o.make_move(recs[ply], p["moves"][ply])), (game, ply)
+                assert out["ply"][ply] == ply + 1 and out["game"][ply] == game
+            else:
+                assert st & 0x800 and np.array_equal(out["boards"][ply], start)
+                assert out["ply"][ply] == 0 and out["game"][ply] == game + 1000
+        assert int(out["counters"][0]) == n and int(out["counters"][6]) == int(p["n_legal"].sum())
+        positions += n
     assert positions > 100
+
+
+def random_positions(R, n, seed):
+    """Mostly unreachable positions: random pieces on random squares, all four kings present most of the time --
+    multiple checks, pins by either opponent, adjacent kings, pawns on every rank."""
+    g = GEOMETRIES[R]
+    rng = np.random.default_rng(seed)
+    valid = [r * R + c for r in range(R) for c in range(R)
+             if not ((r < g.IA or r > R - 1 - g.IA) and (c < g.IA or c > R - 1 - g.IA))]
+    out = []
+    for _ in range(n):
+        rec = g.empty_record()
+        rec[g.off_turn] = rng.integers(0, 4)
+        n_pieces = int(rng.integers(4, 40))
+        squares = rng.choice(valid, size=min(n_pieces, len(valid)), replace=False)
+        kings = list(range(4)) if rng.random() < 0.9 else list(rng.choice(4, size=3, replace=False))
+        for j, sq in enumerate(squares):
+            if j < len(kings):
+                color, ptype = kings[j], 5
+                rec[g.off_king + color] = sq
+            else:
+                color = int(rng.integers(0, 4))
+                ptype = int(rng.choice([0, 0, 0, 1, 2, 3, 4]))
+            rec[sq] = 0x80 | (color << 5) | (ptype << 2)
+        for c in range(4):
+            rec[g.off_rights + c] = 0x80 | (int(rng.integers(0, 4)) << 5)
+        out.append(rec)
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("R", [14, 13, 10, 8])
+def test_rules_warp_on_random_positions(emul, R):
+    o = oracle_for(R)
+    h = Harness(emul, R)
+    recs = random_positions(R, 700, seed=R)
+    n_check = check_positions(h, o, recs)
+    assert n_check > 50  # checks, double checks and pins are the point of this test
+
+
+def test_rules_warp_on_castling_positions(emul):
+    o = oracle_for(14)
+    h = Harness(emul, 14)
+    recs = np.stack(castling_positions(14))
+    check_positions(h, o, recs)
+    castles = 0
+    for rec in recs:
+        castles += sum(1 for m in o.legal_moves(rec) if ((int(m) >> 32) & 0xff) != 196)
+    assert castles >= 8
