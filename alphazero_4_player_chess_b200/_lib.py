@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfpc.so")
+LIB_PATH = os.environ.get("FPC_LIB_PATH") or os.path.join(_HERE, "libfpc.so")  # FPC_LIB_PATH: diagnostics builds (tools/)
 
 FPC_MAX_MOVES = 300
 FPC_OK, FPC_ERR_ARG, FPC_ERR_CUDA, FPC_ERR_MOVE, FPC_ERR_OVERFLOW = 0, -1, -2, -3, -4
@@ -33,6 +33,11 @@ SIGNATURES = {
     "fpc_move_flat_index": (_i, [_i, _u64]),
     "fpc_record_from_fen": (_i, [_i, C.c_char_p, _i, _vp]),
     "fpc_observe": (_i, [_i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "fpc_observe_tracked": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "fpc_dense_track_create": (_vp, [_i, _i]),
+    "fpc_dense_track_invalidate": (None, [_vp]),
+    "fpc_dense_track_destroy": (None, [_vp]),
+    "fpc_shutdown": (_i, []),
     "fpc_join": (_i, [_vp]),
     "fpc_profile_enable": (_i, [_i]),
     "fpc_profile_read": (_i, [_vp, _vp, _vp]),
@@ -42,8 +47,10 @@ SIGNATURES = {
     "fpc_heuristic": (_i, [_i, _vp, _i, _vp, _vp]),
     "fpc_playout_step": (_i, [_i, _vp, _i, _u64, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _vp, _vp, _i, _vp,
                               _vp, _i, _vp]),
+    "fpc_playout_step_tracked": (_i, [_vp, _i, _vp, _i, _u64, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _vp, _vp, _i, _vp,
+                                      _vp, _i, _vp]),
     "fpc_tree_reset": (_i, [_vp, _vp, _vp]),
-    "fpc_tree_select": (_i, [_vp, _i, _vp, _i, _vp]),
+    "fpc_tree_select": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "fpc_tree_expand_backup": (_i, [_vp, _vp, _vp, _vp]),
     "fpc_ctx_create": (_vp, [_i, _i, _i]),
     "fpc_ctx_destroy": (None, [_vp]),

@@ -21,11 +21,11 @@ constexpr int WARPS_PER_BLOCK = 4;  // one warp per game
 constexpr int BLOCK_THREADS = WARPS_PER_BLOCK * 32;
 
 // Dense outputs.  The reference tensors are dense f32 ([n,24,R,R] planes, [n,8R+8,R,R] mask) holding
-// ~40 and ~19 ones per game among 4,704 and 23,520 cells; writing them is the HBM-bound part of the
-// path (113 KB per game at 14x14).  rules_kernel produces them as bit sets (1 bit per cell, 3.5 KB
-// per game, zero-filled and set straight in global memory = L2); expand_kernel streams the bits out as f32.
-// The two kernels run on different streams so that the expansion of one batch overlaps the integer work
-// of the next (FPC_FLAG_ASYNC_DENSE, fpc_join).
+// ~40 and ~19-38 ones per game among 4,704 and 23,520 cells; writing them is the HBM-bound part of the
+// path (113 KB per game at 14x14).  rules_kernel produces them as two short records per game -- the plane cells
+// and the flat action indices that are 1.0 (fpc_rules.cuh: CELL_* / FLAT_*) -- and expand_kernel streams the
+// tensors out: zero fill, then the ones.  The two kernels run on different streams so that the expansion of one
+// batch overlaps the integer work of the next (FPC_FLAG_ASYNC_DENSE, fpc_join).
 
 static_assert(STATUS_IN_CHECK == FPC_STATUS_IN_CHECK && STATUS_CAN_TAKE_KING == FPC_STATUS_CAN_TAKE_KING &&
                   STATUS_OVERFLOW == FPC_STATUS_OVERFLOW && STATUS_FINISHED == FPC_STATUS_FINISHED &&
@@ -40,64 +40,139 @@ static_assert(STATUS_IN_CHECK == FPC_STATUS_IN_CHECK && STATUS_CAN_TAKE_KING == 
 
 // The rules kernel: one warp per game (fpc_rules.cuh).  Legal moves, result, the bit sets of the dense outputs,
 // and (playout) the move choice and make-move.  It touches only the board store and compact per-game outputs.
-template <class G>
-__global__ void __launch_bounds__(BLOCK_THREADS) rules_kernel(const __grid_constant__ ObserveParams P) {
-  __shared__ RulesScratch<G> scratch[WARPS_PER_BLOCK];
+template <class G, int WPB = WARPS_PER_BLOCK>
+__global__ void __launch_bounds__(WPB * 32) rules_kernel(const __grid_constant__ ObserveParams P) {
+  __shared__ RulesScratch<G> scratch[WPB];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int g = blockIdx.x * WARPS_PER_BLOCK + wib;
+  const int g = blockIdx.x * WPB + wib;
   if (g >= P.n) return;
   rules_warp<G>(P, scratch[wib], g, lane);
 }
 
-// bits -> dense f32 (0.0 / 1.0).  One tensor per launch half: games x (words_per_game words ->
-// floats_per_game floats).  A warp takes 32 words of one game per iteration with one coalesced
-// load, hands them round with shuffles and issues 8 store instructions of 512 contiguous bytes.
-// Pure streaming: no shared memory, one pass, HBM-write bound.
-constexpr int EXPAND_THREADS = 128;
-constexpr int EXPAND_ITERS = 1;  // 32-word groups per warp (finer CTAs stream better: tools/sweep.sh)
+// Records -> dense f32 (0.0 / 1.0).  One CTA per game: every thread streams zeros over the game's two tensors
+// (coalesced 16-byte st.global.cs, nothing to wait for: the stores do not depend on any load), the CTA synchronises,
+// and one thread per recorded one writes its 1.0f.  The records are read while the zeros are in flight; the ones land
+// in lines this CTA has just written, so they merge in L2 and HBM sees each line once.  ~12 instructions per 512-byte
+// store instruction: the kernel leaves the issue slots to the rules kernel it overlaps.  HBM-write bound.
+constexpr int EXPAND_THREADS = 448;
 
-struct ExpandHalf {
-  const uint32_t *bits;  // [n][words]
-  float *out;            // [n][floats]
-  int words, stride, floats, groups;  // per game: words used, words allocated, floats, ceil(words / 32)
-};
+template <class G>
+__global__ void __launch_bounds__(EXPAND_THREADS)
+    expand_kernel(const uint16_t *__restrict__ cells, float *__restrict__ planes, const uint16_t *__restrict__ flats,
+                  float *__restrict__ mask, int n) {
+  constexpr int P4 = G::SSZ / 4, M4 = G::ASZ / 4;
+  const int t = threadIdx.x, T = blockDim.x;
+  const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  for (int game = blockIdx.x; game < n; game += gridDim.x) {
+    const uint16_t *gc = planes ? cells + (size_t)game * CELL_STRIDE : nullptr;
+    const uint16_t *gf = mask ? flats + (size_t)game * FLAT_STRIDE : nullptr;
+    const int n_cells = gc ? gc[0] : 0, n_flats = gf ? gf[0] : 0;
+    float *pl = planes + (size_t)game * G::SSZ, *mk = mask + (size_t)game * G::ASZ;
+    if (planes)
+      for (int i = t; i < P4; i += T) __stcs(reinterpret_cast<float4 *>(pl) + i, zero);
+    if (mask)
+      for (int i = t; i < M4; i += T) __stcs(reinterpret_cast<float4 *>(mk) + i, zero);
+    int my_cell[1], my_flat[1];
+    my_cell[0] = t < n_cells ? gc[CELL_FIRST + t] : -1;
+    my_flat[0] = t < n_flats ? gf[FLAT_FIRST + t] : -1;
+    __syncthreads();  // block-wide memory ordering: every zero precedes every one
+    if (my_cell[0] >= 0) pl[my_cell[0]] = 1.0f;
+    if (my_flat[0] >= 0) mk[my_flat[0]] = 1.0f;
+    for (int i = t + T; i < n_cells; i += T) pl[gc[CELL_FIRST + i]] = 1.0f;
+    for (int i = t + T; i < n_flats; i += T) mk[gf[FLAT_FIRST + i]] = 1.0f;
+    __syncthreads();  // the next game of this CTA must not start zeroing before ... (different game: no overlap) -- keeps warps together
+  }
+}
 
-__global__ void __launch_bounds__(512)
-    expand_kernel(const __grid_constant__ ExpandHalf A, const __grid_constant__ ExpandHalf B, int n, int iters) {
-  const int lane = threadIdx.x & 31;
-  const unsigned long long warp = (unsigned long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  const unsigned long long total_a = (unsigned long long)n * A.groups, total_b = (unsigned long long)n * B.groups;
-#pragma unroll 1
-  for (int it = 0; it < iters; ++it) {
-    unsigned long long grp = warp * iters + it;
-    const ExpandHalf *H = &A;
-    if (grp >= total_a) {
-      grp -= total_a;
-      if (grp >= total_b) return;
-      H = &B;
+// The same expansion with the zeros written by the TMA engine: one warp per CTA, a zero tile in shared memory, and per
+// game a handful of cp.async.bulk shared->global copies issued by one lane -- no store instructions through the
+// load/store pipe, next to no issue slots: the SM is left to the rules kernel that overlaps it.  The ones follow once
+// the bulk group has completed (cross-proxy fence between the async-proxy zeros and the generic-proxy ones).
+// V: 0 = wait + ones per game, 1 = no ones (timing only), 2 = two games in flight per CTA (wait_group 1)
+template <class G, int TILE, int V>
+__global__ void __launch_bounds__(32) expand_tma_kernel(const uint16_t *__restrict__ cells, float *__restrict__ planes,
+                                                        const uint16_t *__restrict__ flats, float *__restrict__ mask, int n) {
+  extern __shared__ __align__(128) uint8_t zbuf[];
+  const int lane = threadIdx.x;
+  for (int i = lane; i < TILE / 16; i += 32) reinterpret_cast<uint4 *>(zbuf)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  const uint32_t src = (uint32_t)__cvta_generic_to_shared(zbuf);
+  int pc[5], pf[10];
+  float *ppl = nullptr, *pmk = nullptr;
+  bool have_prev = false;
+  for (int game = blockIdx.x; game < n; game += gridDim.x) {
+    float *pl = planes ? planes + (size_t)game * G::SSZ : nullptr, *mk = mask ? mask + (size_t)game * G::ASZ : nullptr;
+    if (lane == 0) {
+      if (pl)
+        for (int off = 0; off < G::SSZ * 4; off += TILE) {
+          const uint32_t sz = G::SSZ * 4 - off < TILE ? G::SSZ * 4 - off : TILE;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint8_t *>(pl) + off), "r"(src), "r"(sz) : "memory");
+        }
+      if (mk)
+        for (int off = 0; off < G::ASZ * 4; off += TILE) {
+          const uint32_t sz = G::ASZ * 4 - off < TILE ? G::ASZ * 4 - off : TILE;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint8_t *>(mk) + off), "r"(src), "r"(sz) : "memory");
+        }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    const unsigned long long game = grp / H->groups;
-    const int w0 = (int)(grp - game * H->groups) * 32;
-    const uint32_t mine = w0 + lane < H->words ? __ldg(H->bits + game * H->stride + w0 + lane) : 0u;
-    float4 *dst = reinterpret_cast<float4 *>(H->out + game * H->floats);
-    // almost every word is zero (~40 ones among 4,704 cells, ~19 among 23,520): a store whose four
-    // words are all zero needs no shuffle and no bit arithmetic -- warp-uniform test on one ballot
-    const unsigned nz = __ballot_sync(FULL, mine != 0u);
+    if (V == 1) continue;
+    // the records travel while the zeros are written
+    const uint16_t *gc = pl ? cells + (size_t)game * CELL_STRIDE : nullptr;
+    const uint16_t *gf = mk ? flats + (size_t)game * FLAT_STRIDE : nullptr;
+    const int n_cells = gc ? gc[0] : 0, n_flats = gf ? gf[0] : 0;
+    int c[5], f[10];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // store j, lane l: float4 number w0*8 + j*32 + l of this game = word w0 + j*4 + l/8, nibble l%8
-      const int f4 = w0 * 8 + j * 32 + lane;
-      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if ((nz >> (j * 4)) & 15u) {
-        const uint32_t w = __shfl_sync(FULL, mine, j * 4 + (lane >> 3));
-        const uint32_t nib = (w >> ((lane & 7) * 4)) & 15u;
-        v.x = (nib & 1u) ? 1.0f : 0.0f;
-        v.y = (nib & 2u) ? 1.0f : 0.0f;
-        v.z = (nib & 4u) ? 1.0f : 0.0f;
-        v.w = (nib & 8u) ? 1.0f : 0.0f;
+    for (int j = 0; j < 5; ++j) c[j] = lane + 32 * j < n_cells ? gc[CELL_FIRST + lane + 32 * j] : -1;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) f[j] = lane + 32 * j < n_flats ? gf[FLAT_FIRST + lane + 32 * j] : -1;
+    if (V == 2) {
+      // complete the PREVIOUS game while this one's zeros are in flight
+      if (have_prev) {
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          if (pc[j] >= 0) ppl[pc[j]] = 1.0f;
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+          if (pf[j] >= 0) pmk[pf[j]] = 1.0f;
       }
-      if (f4 * 4 < H->floats) __stcs(dst + f4, v);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) pc[j] = c[j];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) pf[j] = f[j];
+      ppl = pl, pmk = mk, have_prev = true;
+      continue;
     }
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (c[j] >= 0) pl[c[j]] = 1.0f;
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+      if (f[j] >= 0) mk[f[j]] = 1.0f;
+  }
+  if (V == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (V == 2 && have_prev) {
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (pc[j] >= 0) ppl[pc[j]] = 1.0f;
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+      if (pf[j] >= 0) pmk[pf[j]] = 1.0f;
   }
 }
 
@@ -172,8 +247,34 @@ int cuda_check(cudaError_t e, const char *what) {
   return fail(FPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-// Per host thread and device: the stream expand_kernel runs on, its events, and the double-buffered
-// bit-set workspace between rules_kernel and expand_kernel.
+// One record pair (plane cells / mask flats) per game, double-buffered: rules_kernel of step t+1 writes one buffer
+// while expand_kernel of step t still reads the other.
+struct Records {
+  uint16_t *cells[2] = {nullptr, nullptr}, *flats[2] = {nullptr, nullptr};
+  size_t games = 0;
+  int release() {
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(cells[i]);
+      cudaFree(flats[i]);
+      cells[i] = flats[i] = nullptr;
+    }
+    games = 0;
+    return FPC_OK;
+  }
+  int reserve(size_t n) {
+    if (n <= games) return FPC_OK;
+    release();
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaMalloc(&cells[i], n * CELL_STRIDE * sizeof(uint16_t)));
+      CK(cudaMalloc(&flats[i], n * FLAT_STRIDE * sizeof(uint16_t)));
+    }
+    games = n;
+    return FPC_OK;
+  }
+};
+
+// Per host thread and device: the streams the two kernels of a dense call run on, their events, and the record
+// workspace between rules_kernel and expand_kernel for calls without a fpc_dense_track.
 struct SideState {
   cudaStream_t side = nullptr;  // expand_kernel: lowest priority
   cudaStream_t hi = nullptr;    // rules_kernel when dense outputs are wanted: highest priority, so that its
@@ -181,21 +282,10 @@ struct SideState {
   cudaEvent_t fork = nullptr;
   cudaEvent_t rules_done[2] = {nullptr, nullptr}, expand_done[2] = {nullptr, nullptr};
   bool expand_recorded[2] = {false, false};
-  uint32_t *bits[2] = {nullptr, nullptr};
-  size_t bits_words = 0;
+  Records ws;
   int parity = 0;
-  int last = -1;  // buffer of the most recent expansion (fpc_join)
-  // Dense tensors whose content is known exactly: the list of ones the latest call left in them
-  // (FPC_FLAG_INCREMENTAL updates such tensors in place instead of rewriting them).
-  struct Tracked {
-    const float *planes = nullptr, *mask = nullptr;
-    int n = 0, R = 0;
-    uint16_t *lists = nullptr;
-    size_t lists_games = 0;
-    unsigned long long stamp = 0;
-  };
-  Tracked tracked[4];
-  unsigned long long stamp = 0;
+  int last = -1;           // event slot of the most recent expansion (fpc_join)
+  bool last_async = false;  // ... which the caller's stream has not been made to wait for (FPC_FLAG_ASYNC_DENSE)
   // optional CUDA-event timing of expand_kernel on its own stream (fpc_profile_enable / _read)
   bool prof_on = false;
   int prof_n = 0;
@@ -203,16 +293,20 @@ struct SideState {
   std::vector<cudaEvent_t> prof_ev_r; // rules_kernel (dense path): start/stop pairs
 };
 constexpr int PROF_MAX = 4096;
-static thread_local SideState g_side[16];
+constexpr int MAX_DEVICES = 16;
+static thread_local SideState g_side[MAX_DEVICES];
 
-static int side_state(SideState **out, size_t words, cudaStream_t st) {
+static int side_state(SideState **out) {
   int dev = 0;
   CK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 16) return fail(FPC_ERR_ARG, "device ordinal out of range");
+  if (dev < 0 || dev >= MAX_DEVICES) return fail(FPC_ERR_ARG, "device ordinal out of range");
   SideState &S = g_side[dev];
   if (!S.side) {
     int least = 0, greatest = 0;
     CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+#ifdef FPC_EXPERIMENT
+    if (getenv("FPC_X_NOPRIO") && atoi(getenv("FPC_X_NOPRIO"))) greatest = least = 0;
+#endif
     CK(cudaStreamCreateWithPriority(&S.side, cudaStreamNonBlocking, least));
     CK(cudaStreamCreateWithPriority(&S.hi, cudaStreamNonBlocking, greatest));
     CK(cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming));
@@ -221,150 +315,197 @@ static int side_state(SideState **out, size_t words, cudaStream_t st) {
       CK(cudaEventCreateWithFlags(&S.expand_done[i], cudaEventDisableTiming));
     }
   }
-  if (words > S.bits_words) {
-    // growing the workspace: earlier launches may still use the old one
-    if (S.bits[0]) {
-      CK(cudaStreamSynchronize(st));
-      CK(cudaStreamSynchronize(S.side));
-      cudaFree(S.bits[0]);
-      cudaFree(S.bits[1]);
-      S.bits[0] = S.bits[1] = nullptr;
-      S.bits_words = 0;
-    }
-    CK(cudaMalloc(&S.bits[0], words * sizeof(uint32_t)));
-    CK(cudaMalloc(&S.bits[1], words * sizeof(uint32_t)));
-    S.bits_words = words;
-  }
   *out = &S;
   return FPC_OK;
 }
 
-struct DenseOut {
-  float *planes, *mask;
-  int flags;
-};
-
-// The record slot of a (planes, mask, n, R) output set: an existing one (content known: *known = true) or the least
-// recently used one, re-targeted (content unknown until a full dense call has run).
-static int tracked_slot(SideState *S, const DenseOut &d, int n, int R, cudaStream_t st, SideState::Tracked **out, bool *known) {
-  SideState::Tracked *hit = nullptr, *lru = &S->tracked[0];
-  for (auto &t : S->tracked) {
-    if (t.lists && t.planes == d.planes && t.mask == d.mask && t.n == n && t.R == R) hit = &t;
-    if (t.stamp < lru->stamp) lru = &t;
-  }
-  *known = hit != nullptr;
-  SideState::Tracked *t = hit ? hit : lru;
-  if (!hit) {
-    if (t->lists_games < (size_t)n) {
-      if (t->lists) {
-        CK(cudaStreamSynchronize(st));
-        CK(cudaStreamSynchronize(S->side));
-        CK(cudaStreamSynchronize(S->hi));
-        cudaFree(t->lists);
-        t->lists = nullptr;
-      }
-      CK(cudaMalloc(&t->lists, (size_t)n * LIST_STRIDE * sizeof(uint16_t)));
-      t->lists_games = (size_t)n;
+// Releases everything this host thread holds on the current device (fpc_shutdown).
+static int side_release() {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEVICES) return fail(FPC_ERR_ARG, "device ordinal out of range");
+  SideState &S = g_side[dev];
+  if (S.side) {
+    CK(cudaStreamSynchronize(S.side));
+    CK(cudaStreamSynchronize(S.hi));
+    cudaStreamDestroy(S.side);
+    cudaStreamDestroy(S.hi);
+    cudaEventDestroy(S.fork);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(S.rules_done[i]);
+      cudaEventDestroy(S.expand_done[i]);
     }
-    t->planes = d.planes, t->mask = d.mask, t->n = n, t->R = R;
   }
-  t->stamp = ++S->stamp;
-  *out = t;
+  S.ws.release();
+  for (auto &e : S.prof_ev) cudaEventDestroy(e);
+  for (auto &e : S.prof_ev_r) cudaEventDestroy(e);
+  S = SideState();
   return FPC_OK;
 }
 
-// rules_kernel on the caller's stream; expand_kernel on the side stream once the rules kernel has
-// written the bit sets.  Unless FPC_FLAG_ASYNC_DENSE is set the caller's stream then waits for the
-// expansion.  after_rules (may be a no-op) runs right after the rules kernel is enqueued: the
-// host-buffer entry points start their device-to-host copies of the compact results there.
+}  // namespace fpc
+
+// Explicit handle for resident dense tensors (FPC_FLAG_INCREMENTAL): it owns the records of the ones the latest dense
+// call through it left in ONE planes tensor and / or ONE mask tensor.  Nothing is keyed on pointer identity alone: a
+// handle only vouches for tensors it was itself used with since its creation or last invalidation.
+struct fpc_dense_track {
+  unsigned magic;
+  int device, R, n;
+  fpc::Records rec;
+  // per tensor: the pointer the record describes, which buffer holds the record, whether the content is known
+  const float *planes, *mask;
+  int cur_cells, cur_flats;
+  bool known_planes, known_mask;
+};
+
+namespace fpc {
+constexpr unsigned TRACK_MAGIC = 0x46504354u;  // "FPCT"
+
+struct DenseOut {
+  float *planes, *mask;
+  int flags;
+  fpc_dense_track *track;
+};
+
+#ifdef FPC_EXPERIMENT
+// Diagnostics build only (tools/overlap_probe.py): knobs that change how the two kernels of a dense step are launched.
+static int xknob(const char *name) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+template <class G>
+static void launch_rules_x(int n, cudaStream_t st, const ObserveParams &p) {
+  switch (xknob("FPC_X_RWARPS")) {
+    case 1: rules_kernel<G, 1><<<n, 32, 0, st>>>(p); break;
+    case 2: rules_kernel<G, 2><<<(n + 1) / 2, 64, 0, st>>>(p); break;
+    case 8: rules_kernel<G, 8><<<(n + 7) / 8, 256, 0, st>>>(p); break;
+    default: rules_kernel<G, 4><<<(n + 3) / 4, 128, 0, st>>>(p); break;
+  }
+}
+#endif
+
+// rules_kernel on a high-priority stream forked from the caller's; expand_kernel on the side stream once the rules
+// kernel has written the records.  Unless FPC_FLAG_ASYNC_DENSE is set the caller's stream then waits for the
+// expansion.  after_rules (may be a no-op) runs right after the rules kernel is enqueued: the host-buffer entry
+// points start their device-to-host copies of the compact results there.
 template <class G, class F>
 static int launch_observe(ObserveParams p, DenseOut d, cudaStream_t st, F after_rules) {
   if (p.n == 0) return FPC_OK;
   const bool dense = d.planes || d.mask;
-  SideState *S = nullptr;
-  int b = 0;
-  if (dense) {
-    if ((reinterpret_cast<uintptr_t>(d.planes) | reinterpret_cast<uintptr_t>(d.mask)) & 15)
-      return fail(FPC_ERR_ARG, "planes / mask must be 16-byte aligned");
-    const size_t pw = (size_t)p.n * G::PLANE_STRIDE, mw = (size_t)p.n * G::MASK_STRIDE;
-    int rc = side_state(&S, pw + mw, st);
-    if (rc != FPC_OK) return rc;
-    SideState::Tracked *trk = nullptr;
-    bool known = false;
-    rc = tracked_slot(S, d, p.n, G::R, st, &trk, &known);
-    if (rc != FPC_OK) return rc;
-    p.lists = trk->lists;
-    p.list_cells = d.planes != nullptr;
-    p.list_flats = d.mask != nullptr;
-    if ((d.flags & FPC_FLAG_INCREMENTAL) && known) {
-      // the tensors hold exactly the recorded ones: clear those, set the new ones, no expansion.  A still running
-      // expansion into the same tensors (an earlier FPC_FLAG_ASYNC_DENSE call) must finish first.
-      if (S->last >= 0) CK(cudaStreamWaitEvent(st, S->expand_done[S->last], 0));
-      p.inc_planes = d.planes;
-      p.inc_mask = d.mask;
-      const int blocks_inc = (p.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-      rules_kernel<G><<<blocks_inc, BLOCK_THREADS, 0, st>>>(p);
-      CK(cudaGetLastError());
-      return after_rules();
-    }
-    b = S->parity;
-    S->parity ^= 1;
-    p.plane_bits = d.planes ? S->bits[b] : nullptr;
-    p.mask_bits = d.mask ? S->bits[b] + pw : nullptr;
-  }
   const int blocks = (p.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
   if (!dense) {
     rules_kernel<G><<<blocks, BLOCK_THREADS, 0, st>>>(p);
     CK(cudaGetLastError());
     return after_rules();
   }
-  // fork: caller's stream -> high-priority stream (rules) -> back to the caller's stream; the
-  // expansion that last read this bit buffer must be done before the rules kernel rewrites it
+  if ((reinterpret_cast<uintptr_t>(d.planes) | reinterpret_cast<uintptr_t>(d.mask)) & 15)
+    return fail(FPC_ERR_ARG, "planes / mask must be 16-byte aligned");
+  SideState *S = nullptr;
+  int rc = side_state(&S);
+  if (rc != FPC_OK) return rc;
+  fpc_dense_track *T = d.track;
+  if (T) {
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (T->magic != TRACK_MAGIC) return fail(FPC_ERR_ARG, "fpc_dense_track: not a live handle");
+    if (T->device != dev || T->R != G::R || T->n != p.n) return fail(FPC_ERR_ARG, "fpc_dense_track: made for another device / board size / batch");
+    // a handle follows one planes tensor and one mask tensor; being used with another one starts over for that tensor
+    if (d.planes && d.planes != T->planes) T->planes = d.planes, T->known_planes = false;
+    if (d.mask && d.mask != T->mask) T->mask = d.mask, T->known_mask = false;
+    const bool inc = (d.flags & FPC_FLAG_INCREMENTAL) && (!d.planes || T->known_planes) && (!d.mask || T->known_mask);
+    if (inc) {
+      // the tensors hold exactly the recorded ones: clear those, set the new ones, no expansion.  A still running
+      // expansion into the same tensors (an earlier FPC_FLAG_ASYNC_DENSE call) must finish first.
+      if (S->last >= 0 && S->last_async) CK(cudaStreamWaitEvent(st, S->expand_done[S->last], 0));
+      p.cells = d.planes ? T->rec.cells[T->cur_cells] : nullptr;
+      p.flats = d.mask ? T->rec.flats[T->cur_flats] : nullptr;
+      p.inc_planes = d.planes;
+      p.inc_mask = d.mask;
+      rules_kernel<G><<<blocks, BLOCK_THREADS, 0, st>>>(p);
+      CK(cudaGetLastError());
+      return after_rules();
+    }
+  }
+  // full rewrite: the records go to the buffer the previous expansion is not reading
+  const int b = S->parity;
+  S->parity ^= 1;
+  if (T) {
+    if (d.planes) T->cur_cells ^= 1, p.cells = T->rec.cells[T->cur_cells], T->known_planes = true;
+    if (d.mask) T->cur_flats ^= 1, p.flats = T->rec.flats[T->cur_flats], T->known_mask = true;
+  } else {
+    if ((size_t)p.n > S->ws.games) {  // growing the workspace: earlier launches may still use the old one
+      CK(cudaStreamSynchronize(st));
+      CK(cudaStreamSynchronize(S->side));
+      CK(cudaStreamSynchronize(S->hi));
+      rc = S->ws.reserve((size_t)p.n);
+      if (rc != FPC_OK) return rc;
+    }
+    p.cells = d.planes ? S->ws.cells[b] : nullptr;
+    p.flats = d.mask ? S->ws.flats[b] : nullptr;
+  }
+  // fork: caller's stream -> high-priority stream (rules) -> back to the caller's stream; the expansion that last
+  // read this record buffer (two dense calls ago) must be done before the rules kernel rewrites it
   CK(cudaEventRecord(S->fork, st));
   CK(cudaStreamWaitEvent(S->hi, S->fork, 0));
   if (S->expand_recorded[b]) CK(cudaStreamWaitEvent(S->hi, S->expand_done[b], 0));
-  // Both kernels ask for the same shared-memory carveout: CTAs of rules_kernel (24 KB of shared memory each) and of
+#ifdef FPC_EXPERIMENT
+  if (xknob("FPC_X_SERIAL") && S->last >= 0) CK(cudaStreamWaitEvent(S->hi, S->expand_done[S->last], 0));
+#endif
+  // Both kernels ask for the same shared-memory carveout: CTAs of rules_kernel (14 KB of shared memory each) and of
   // expand_kernel (none) share SMs, and an SM only changes its L1 / shared split when it is empty.
   {
-    static thread_local bool carveout_set[16] = {false};
+    static thread_local bool carveout_set[MAX_DEVICES] = {false};
     int dev = 0;
     CK(cudaGetDevice(&dev));
-    const char *env = getenv("FPC_CARVEOUT");
-    const int pct = env ? atoi(env) : 100;
-    if (dev >= 0 && dev < 16 && !carveout_set[dev] && pct >= 0) {
-      CK(cudaFuncSetAttribute(rules_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-      CK(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    if (dev >= 0 && dev < MAX_DEVICES && !carveout_set[dev]) {
+      CK(cudaFuncSetAttribute(rules_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CK(cudaFuncSetAttribute(expand_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       carveout_set[dev] = true;
     }
   }
-  const bool prof_r = S->prof_on && S->prof_n < PROF_MAX;
-  if (prof_r) CK(cudaEventRecord(S->prof_ev_r[2 * S->prof_n], S->hi));
+  const bool prof = S->prof_on && S->prof_n < PROF_MAX;
+  if (prof) CK(cudaEventRecord(S->prof_ev_r[2 * S->prof_n], S->hi));
+#ifdef FPC_EXPERIMENT
+  if (!xknob("FPC_X_SKIPRULES")) launch_rules_x<G>(p.n, S->hi, p);
+#else
   rules_kernel<G><<<blocks, BLOCK_THREADS, 0, S->hi>>>(p);
+#endif
   CK(cudaGetLastError());
-  if (prof_r) CK(cudaEventRecord(S->prof_ev_r[2 * S->prof_n + 1], S->hi));
+  if (prof) CK(cudaEventRecord(S->prof_ev_r[2 * S->prof_n + 1], S->hi));
   CK(cudaEventRecord(S->rules_done[b], S->hi));
   CK(cudaStreamWaitEvent(st, S->rules_done[b], 0));
-  int rc = after_rules();
+  rc = after_rules();
   if (rc != FPC_OK) return rc;
-  {
-    CK(cudaStreamWaitEvent(S->side, S->rules_done[b], 0));
-    ExpandHalf A{p.plane_bits, d.planes, G::PLANE_WORDS, G::PLANE_STRIDE, G::SSZ, d.planes ? (G::PLANE_WORDS + 31) / 32 : 0};
-    ExpandHalf B{p.mask_bits, d.mask, G::MASK_WORDS, G::MASK_STRIDE, G::ASZ, d.mask ? (G::MASK_WORDS + 31) / 32 : 0};
-    const unsigned long long groups = (unsigned long long)p.n * (A.groups + B.groups);
-    static const int iters = getenv("FPC_EXPAND_ITERS") ? atoi(getenv("FPC_EXPAND_ITERS")) : EXPAND_ITERS;
-    static const int threads = getenv("FPC_EXPAND_THREADS") ? atoi(getenv("FPC_EXPAND_THREADS")) : EXPAND_THREADS;
-    const unsigned long long warps = (groups + iters - 1) / iters;
-    const unsigned long long grid = (warps + threads / 32 - 1) / (threads / 32);
-    const bool prof = S->prof_on && S->prof_n < PROF_MAX;
-    if (prof) CK(cudaEventRecord(S->prof_ev[2 * S->prof_n], S->side));
-    expand_kernel<<<(unsigned)grid, threads, 0, S->side>>>(A, B, p.n, iters);
-    CK(cudaGetLastError());
-    if (prof) CK(cudaEventRecord(S->prof_ev[2 * S->prof_n++ + 1], S->side));
-    CK(cudaEventRecord(S->expand_done[b], S->side));
-    S->expand_recorded[b] = true;
-    S->last = b;
-    if (!(d.flags & FPC_FLAG_ASYNC_DENSE)) CK(cudaStreamWaitEvent(st, S->expand_done[b], 0));
+  CK(cudaStreamWaitEvent(S->side, S->rules_done[b], 0));
+  if (prof) CK(cudaEventRecord(S->prof_ev[2 * S->prof_n], S->side));
+  int threads = EXPAND_THREADS;
+#ifdef FPC_EXPERIMENT
+  if (xknob("FPC_X_ETHREADS")) threads = xknob("FPC_X_ETHREADS");
+  if (xknob("FPC_X_NOEXPAND")) threads = 0;
+  if (xknob("FPC_X_TMA")) {
+    const int per_sm = xknob("FPC_X_TMA");
+    const int grid = p.n < 148 * per_sm ? p.n : 148 * per_sm, v = xknob("FPC_X_TMAV"), tile = xknob("FPC_X_TILE");
+#define TMA_ARGS p.cells, d.planes, p.flats, d.mask, p.n
+    if (tile == 32) {
+      static bool attr = false;
+      if (!attr) cudaFuncSetAttribute(expand_tma_kernel<G, 32768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768), attr = true;
+      expand_tma_kernel<G, 32768, 2><<<grid, 32, 32768, S->side>>>(TMA_ARGS);
+    } else if (tile == 4) expand_tma_kernel<G, 4096, 2><<<grid, 32, 4096, S->side>>>(TMA_ARGS);
+    else if (v == 1) expand_tma_kernel<G, 16384, 1><<<grid, 32, 16384, S->side>>>(TMA_ARGS);
+    else if (v == 2) expand_tma_kernel<G, 16384, 2><<<grid, 32, 16384, S->side>>>(TMA_ARGS);
+    else expand_tma_kernel<G, 16384, 0><<<grid, 32, 16384, S->side>>>(TMA_ARGS);
+    threads = 0;
   }
+  if (threads)
+#endif
+  expand_kernel<G><<<p.n, threads, 0, S->side>>>(p.cells, d.planes, p.flats, d.mask, p.n);
+  CK(cudaGetLastError());
+  if (prof) CK(cudaEventRecord(S->prof_ev[2 * S->prof_n++ + 1], S->side));
+  CK(cudaEventRecord(S->expand_done[b], S->side));
+  S->expand_recorded[b] = true;
+  S->last = b;
+  S->last_async = (d.flags & FPC_FLAG_ASYNC_DENSE) != 0;
+  if (!S->last_async) CK(cudaStreamWaitEvent(st, S->expand_done[b], 0));
   return FPC_OK;
 }
 template <class G>
@@ -527,7 +668,7 @@ int fpc_record_from_fen(int R, const char *fen, int honour_castling, uint8_t *h_
 
 int fpc_profile_enable(int on) {
   SideState *S = nullptr;
-  int rc = side_state(&S, 0, nullptr);
+  int rc = side_state(&S);
   if (rc != FPC_OK) return rc;
   if (on && S->prof_ev.empty()) {
     S->prof_ev.resize(2 * PROF_MAX);
@@ -542,7 +683,7 @@ int fpc_profile_enable(int on) {
 
 int fpc_profile_read(int *launches, double *expand_ms, double *rules_ms) {
   SideState *S = nullptr;
-  int rc = side_state(&S, 0, nullptr);
+  int rc = side_state(&S);
   if (rc != FPC_OK) return rc;
   CK(cudaStreamSynchronize(S->side));
   CK(cudaStreamSynchronize(S->hi));
@@ -563,15 +704,54 @@ int fpc_profile_read(int *launches, double *expand_ms, double *rules_ms) {
 int fpc_join(void *stream) {
   int dev = 0;
   CK(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 16) return fail(FPC_ERR_ARG, "device ordinal out of range");
+  if (dev < 0 || dev >= MAX_DEVICES) return fail(FPC_ERR_ARG, "device ordinal out of range");
   SideState &S = g_side[dev];
   if (S.last >= 0) CK(cudaStreamWaitEvent((cudaStream_t)stream, S.expand_done[S.last], 0));
   return FPC_OK;
 }
 
-int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_t *d_flat, int32_t *d_counts,
-                int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all, float *d_mask, int flags,
-                void *stream) {
+int fpc_shutdown(void) { return side_release(); }
+
+fpc_dense_track *fpc_dense_track_create(int R, int n) {
+  if (!fpc_supported(R) || n <= 0) {
+    fail(FPC_ERR_ARG, "fpc_dense_track_create: bad argument");
+    return nullptr;
+  }
+  int dev = 0;
+  if (cuda_check(cudaGetDevice(&dev), "cudaGetDevice") != FPC_OK) return nullptr;
+  fpc_dense_track *t = new fpc_dense_track();
+  t->magic = TRACK_MAGIC;
+  t->device = dev, t->R = R, t->n = n;
+  t->planes = t->mask = nullptr;
+  t->cur_cells = t->cur_flats = 0;
+  t->known_planes = t->known_mask = false;
+  if (t->rec.reserve((size_t)n) != FPC_OK) {
+    t->rec.release();
+    delete t;
+    return nullptr;
+  }
+  return t;
+}
+
+void fpc_dense_track_invalidate(fpc_dense_track *t) {
+  if (t && t->magic == TRACK_MAGIC) t->known_planes = t->known_mask = false;
+}
+
+void fpc_dense_track_destroy(fpc_dense_track *t) {
+  if (!t || t->magic != TRACK_MAGIC) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaSetDevice(t->device);
+  cudaDeviceSynchronize();  // kernels may still read the records
+  t->rec.release();
+  cudaSetDevice(dev);
+  t->magic = 0;
+  delete t;
+}
+
+int fpc_observe_tracked(fpc_dense_track *track, int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_t *d_flat,
+                        int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all, float *d_mask,
+                        int flags, void *stream) {
   if (n < 0 || (n > 0 && !d_boards)) return fail(FPC_ERR_ARG, "fpc_observe: bad boards/n");
   ObserveParams p{};
   p.boards_in = d_boards;
@@ -583,7 +763,14 @@ int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_
   p.status = d_status;
   p.k = d_k;
   p.k_all = k_all;
-  return do_observe(R, p, DenseOut{d_planes, d_mask, flags}, (cudaStream_t)stream);
+  return do_observe(R, p, DenseOut{d_planes, d_mask, flags, track}, (cudaStream_t)stream);
+}
+
+int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_t *d_flat, int32_t *d_counts,
+                int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all, float *d_mask, int flags,
+                void *stream) {
+  return fpc_observe_tracked(nullptr, R, d_boards, n, d_moves, d_flat, d_counts, d_status, d_planes, d_k, k_all, d_mask,
+                             flags, stream);
 }
 
 int fpc_encode(int R, const uint8_t *d_boards, int n, const int32_t *d_k, int k_all, float *d_planes, int flags,
@@ -637,15 +824,23 @@ static int playout_params(ObserveParams &p, uint8_t *d_boards, int n, uint64_t s
   return FPC_OK;
 }
 
-int fpc_playout_step(int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d_game, int32_t *d_ply,
-                     const uint8_t *d_start, int max_plies, uint64_t game_stride, uint64_t *d_chosen,
-                     int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all,
-                     float *d_mask, uint64_t *d_counters, int flags, void *stream) {
+int fpc_playout_step_tracked(fpc_dense_track *track, int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d_game,
+                             int32_t *d_ply, const uint8_t *d_start, int max_plies, uint64_t game_stride, uint64_t *d_chosen,
+                             int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all,
+                             float *d_mask, uint64_t *d_counters, int flags, void *stream) {
   ObserveParams p;
   int rc = playout_params(p, d_boards, n, seed, d_game, d_ply, d_start, max_plies, game_stride, d_chosen, d_counts,
                           d_status, d_k, k_all, d_counters);
   if (rc != FPC_OK) return rc;
-  return do_observe(R, p, DenseOut{d_planes, d_mask, flags}, (cudaStream_t)stream);
+  return do_observe(R, p, DenseOut{d_planes, d_mask, flags, track}, (cudaStream_t)stream);
+}
+
+int fpc_playout_step(int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d_game, int32_t *d_ply,
+                     const uint8_t *d_start, int max_plies, uint64_t game_stride, uint64_t *d_chosen,
+                     int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all,
+                     float *d_mask, uint64_t *d_counters, int flags, void *stream) {
+  return fpc_playout_step_tracked(nullptr, R, d_boards, n, seed, d_game, d_ply, d_start, max_plies, game_stride, d_chosen,
+                                  d_counts, d_status, d_planes, d_k, k_all, d_mask, d_counters, flags, stream);
 }
 
 // ---- host-buffer context ---------------------------------------------------------------------
@@ -835,7 +1030,7 @@ int fpc_host_playout_step(fpc_ctx *c, uint8_t *h_boards, int n, uint64_t seed, u
     rc = playout_params(p, m_boards, n, seed, m_game, m_ply, c->d_start, max_plies, game_stride, nullptr, m_counts,
                         m_status, nullptr, k_all, nullptr);
     if (rc != FPC_OK) return rc;
-    rc = do_observe(c->R, p, DenseOut{d_planes, d_mask, flags}, c->stream);
+    rc = do_observe(c->R, p, DenseOut{d_planes, d_mask, flags, nullptr}, c->stream);
     if (rc != FPC_OK) return rc;
     CK(cudaStreamSynchronize(c->stream));
     return FPC_OK;
@@ -847,7 +1042,7 @@ int fpc_host_playout_step(fpc_ctx *c, uint8_t *h_boards, int n, uint64_t seed, u
                       c->d_counts, c->d_status, nullptr, k_all, nullptr);
   if (rc != FPC_OK) return rc;
   // the compact results go back to the host while the dense outputs are still being written
-  rc = do_observe(c->R, p, DenseOut{d_planes, d_mask, flags}, c->stream, [&]() -> int {
+  rc = do_observe(c->R, p, DenseOut{d_planes, d_mask, flags, nullptr}, c->stream, [&]() -> int {
     CK(cudaMemcpyAsync(h_boards, c->d_boards, N * c->rec, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(h_game, c->d_game, N * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(h_ply, c->d_ply, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

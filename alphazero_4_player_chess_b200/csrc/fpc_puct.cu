@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) tree_descend_kernel(const fpc_
 }
 
 // The reference rotates a whole leaf batch by the colour of states[0] (src/cpp/board.cpp:354-355,
-// mcts.py:69): k[g] <- side to move of the first live leaf.
+// mcts.py:69), states = the leaves that are NOT terminal (mcts.py:18-26 drops terminal leaves before the batch is
+// built): k[g] <- side to move of the first leaf whose status (already computed) says IN_PROGRESS.
 template <class G>
 __global__ void __launch_bounds__(1024) tree_batch_k_kernel(const fpc_tree T) {
   __shared__ int first;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(1024) tree_batch_k_kernel(const fpc_tree T) {
   __syncthreads();
   int mine = 0x7fffffff;
   for (int g = threadIdx.x; g < T.n_games; g += blockDim.x)
-    if (T.leaf[g] >= 0) {
+    if (T.leaf[g] >= 0 && (T.leaf_status[g] & FPC_STATUS_RESULT_MASK) == 0) {
       mine = g;
       break;
     }
@@ -353,7 +354,7 @@ int fpc_tree_reset(const fpc_tree *t, const uint8_t *d_root_boards, void *stream
   return cuda_check(cudaGetLastError(), "tree_reset_kernel launch");
 }
 
-int fpc_tree_select(const fpc_tree *t, int batch_rotation, float *d_planes, int flags, void *stream) {
+int fpc_tree_select(const fpc_tree *t, int batch_rotation, float *d_planes, int flags, fpc_dense_track *track, void *stream) {
   int rc = check_tree(t, "fpc_tree_select");
   if (rc != FPC_OK) return rc;
   if (t->n_games == 0) return FPC_OK;
@@ -362,12 +363,18 @@ int fpc_tree_select(const fpc_tree *t, int batch_rotation, float *d_planes, int 
   FPC_DISPATCH(t->R, (tree_descend_kernel<G><<<blocks, SEL_WARPS * 32, 0, st>>>(*t)));
   CK(cudaGetLastError());
   if (batch_rotation) {
+    // the batch rotation is that of the first NON-terminal leaf: results first, then k, then the planes
+    rc = fpc_observe(t->R, t->leaf_boards, t->n_games, nullptr, t->leaf_flat, t->leaf_counts, t->leaf_status, nullptr,
+                     nullptr, 0, nullptr, 0, stream);
+    if (rc != FPC_OK) return rc;
     FPC_DISPATCH(t->R, (tree_batch_k_kernel<G><<<1, 1024, 0, st>>>(*t)));
     CK(cudaGetLastError());
+    return fpc_observe_tracked(track, t->R, t->leaf_boards, t->n_games, nullptr, nullptr, nullptr, nullptr, d_planes, t->k, 0,
+                               nullptr, flags, stream);
   }
   // legal moves + GetGameResult + planes of the leaf batch: the environment's rules kernel
-  return fpc_observe(t->R, t->leaf_boards, t->n_games, nullptr, t->leaf_flat, t->leaf_counts, t->leaf_status, d_planes,
-                     t->k, 0, nullptr, flags, stream);
+  return fpc_observe_tracked(track, t->R, t->leaf_boards, t->n_games, nullptr, t->leaf_flat, t->leaf_counts, t->leaf_status,
+                             d_planes, t->k, 0, nullptr, flags, stream);
 }
 
 int fpc_tree_expand_backup(const fpc_tree *t, const float *d_logits, const float *d_values, void *stream) {

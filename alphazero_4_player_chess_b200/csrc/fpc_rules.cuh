@@ -31,15 +31,14 @@ struct ObserveParams {
   int32_t *flat;        // [n][MAX_MOVES] or null
   int32_t *counts;      // [n] or null
   int32_t *status;      // [n] or null
-  uint32_t *plane_bits; // [n][PLANE_STRIDE] or null: input planes, 1 bit per cell
   const int32_t *k;     // [n] or null
   int k_all;            // -1: own turn
-  uint32_t *mask_bits;  // [n][MASK_STRIDE] or null: legal-move mask, 1 bit per action
-  // Record of the ones a dense call leaves in the caller's tensors: [n][LIST_STRIDE] u16 (in: what the tensors
-  // hold now, out: what they hold after this call).  With inc_planes / inc_mask set the tensors are updated in
-  // place -- previous ones cleared, current ones set -- instead of being rewritten (FPC_FLAG_INCREMENTAL).
-  uint16_t *lists;
-  int list_cells, list_flats;  // which halves of the record this call maintains (planes / mask requested)
+  // The ones of the dense outputs of this call, one record per game and tensor: cells [n][CELL_STRIDE] u16 (the
+  // cells of the input planes), flats [n][FLAT_STRIDE] u16 (the flat indices of the legal-move mask); null = tensor
+  // not asked for.  expand_kernel turns the records into the dense f32 tensors (zero fill + ones).  With inc_planes /
+  // inc_mask set the record is also read (in: what the tensor holds now) and the tensor is updated in place --
+  // previous ones cleared, current ones set -- instead of being rewritten (FPC_FLAG_INCREMENTAL).
+  uint16_t *cells, *flats;
   float *inc_planes, *inc_mask;
   // playout
   int playout;
@@ -53,9 +52,11 @@ struct ObserveParams {
   unsigned long long *counters;
 };
 
-// List of one game (u16 units): [0] number of mask entries, [1] number of plane entries, [2, 2 + 160) plane cell indices ch*R*R + row*R + col (already
-// rotated), [168, 468) flat action indices; 472 u16 = 944 B.  Both parts start on a 16-byte boundary.
-constexpr int LIST_PLANES = 2, LIST_MAX_CELLS = 160, LIST_FLAT = 168, LIST_STRIDE = 472;
+// Records of one game (u16 units, 16-byte aligned parts): [0] the number of entries, [8, ...) the entries --
+// plane cell indices ch*R*R + row*R + col (already rotated; at most one per on-board square) or flat action indices
+// (at most MAX_MOVES; the four promotions of a pawn move share one).
+constexpr int CELL_FIRST = 8, CELL_MAX = 160, CELL_STRIDE = CELL_FIRST + CELL_MAX;      // 336 B
+constexpr int FLAT_FIRST = 8, FLAT_STRIDE = FLAT_FIRST + ((MAX_MOVES + 7) / 8) * 8;    // 624 B
 constexpr int STATUS_IN_CHECK = 0x100, STATUS_CAN_TAKE_KING = 0x200, STATUS_OVERFLOW = 0x400, STATUS_FINISHED = 0x800,
               STATUS_CHECK = 0x1000;
 
@@ -108,7 +109,8 @@ struct alignas(16) RulesScratch {
   uint8_t mb[256];                // byte mailbox (rows), WALL outside the board
   uint8_t rec[256];               // raw record staging (in and out)
   uint16_t plist[160];            // the mover's pieces: mailbox square | piece byte << 8
-  uint16_t list[LIST_STRIDE];     // the ones this call leaves in the dense tensors
+  uint16_t cells[CELL_STRIDE];    // the ones this call leaves in the planes tensor
+  uint16_t flats[FLAT_STRIDE];    // ... and in the mask tensor
   uint32_t pinbits[8];            // mailbox bit set: the mover's pieces pinned to its king
   uint32_t tbits[8];              // mailbox bit set: squares that answer a single check (the checker + the squares between)
   uint8_t rights[4];
@@ -333,7 +335,7 @@ __device__ void rules_warp(const ObserveParams &P, RulesScratch<G> &s, const int
   const uint64_t game_id = P.playout ? P.game[g] : 0;
   const int ply = P.playout ? P.ply[g] : 0;
 
-  // ---- stage the record; line tables <- walls; bit sets of the dense outputs <- 0 (in global memory) -------------
+  // ---- stage the record; line tables <- walls -------------------------------------------------------------------
   if (lane < G::REC / 16)
     reinterpret_cast<uint4 *>(s.rec)[lane] = reinterpret_cast<const uint4 *>(P.boards_in + (size_t)g * G::REC)[lane];
   s.tabA[lane] = kWalls<G>.w[lane];
@@ -342,12 +344,6 @@ __device__ void rules_warp(const ObserveParams &P, RulesScratch<G> &s, const int
   s.tabB[lane + 32] = 0;
   if (lane < 8) s.pinbits[lane] = 0, s.tbits[lane] = 0;
   if (lane < 4) s.king[lane] = NO_SQ;
-  uint32_t *g_planes = P.plane_bits ? P.plane_bits + (size_t)g * G::PLANE_STRIDE : nullptr;
-  uint32_t *g_mask = P.mask_bits ? P.mask_bits + (size_t)g * G::MASK_STRIDE : nullptr;
-  if (g_planes)
-    for (int i = lane; i < G::PLANE_STRIDE / 4; i += 32) reinterpret_cast<uint4 *>(g_planes)[i] = make_uint4(0, 0, 0, 0);
-  if (g_mask)
-    for (int i = lane; i < G::MASK_STRIDE / 4; i += 32) reinterpret_cast<uint4 *>(g_mask)[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
   const int turn = s.rec[G::OFF_TURN] & 3;
   const int my_team = turn & 1, enemy_team = my_team ^ 1;
@@ -390,7 +386,7 @@ __device__ void rules_warp(const ObserveParams &P, RulesScratch<G> &s, const int
   __syncwarp();
 
   // ---- every piece: line tables, king squares, the mover's piece list, the input-plane cells ----------------------
-  const bool want_planes = g_planes || (P.lists && P.list_cells);
+  const bool want_planes = P.cells != nullptr;
   int rot = 0;
   if (want_planes) {
     rot = P.k ? P.k[g] : (P.k_all < 0 ? turn : P.k_all);
@@ -434,8 +430,7 @@ __device__ void rules_warp(const ObserveParams &P, RulesScratch<G> &s, const int
         const int rr = rot == 0 ? r : (rot == 1 ? R - 1 - c : (rot == 2 ? R - 1 - r : c));
         const int cc = rot == 0 ? c : (rot == 1 ? r : (rot == 2 ? R - 1 - c : R - 1 - r));
         const int bit = ch * G::NSQ + rr * R + cc;
-        if (g_planes) atomicOr(&g_planes[bit >> 5], 1u << (bit & 31));
-        if (i < LIST_MAX_CELLS) s.list[LIST_PLANES + i] = (uint16_t)bit;
+        if (i < CELL_MAX) s.cells[CELL_FIRST + i] = (uint16_t)bit;
       }
     }
     const unsigned ob = __ballot_sync(FULL, own);
@@ -638,8 +633,8 @@ __device__ void rules_warp(const ObserveParams &P, RulesScratch<G> &s, const int
     if (P.playout && result == 0)
       pick = (uint32_t)(((mix64(P.seed, game_id, (uint64_t)ply) >> 32) * (uint64_t)n_legal) >> 32);
     const bool want_lists = P.moves || P.flat;
-    const bool want_flats = P.lists && P.list_flats;
-    if (want_lists || g_mask || P.playout || want_flats) {
+    const bool want_flats = P.flats != nullptr;
+    if (want_lists || P.playout || want_flats) {
       // pad to a multiple of four with keys above every real one: the rank loop compares four keys per load
       if (lane < 4) s.moves[n_legal + lane] = 0xffffffffu;
       __syncwarp();
@@ -648,8 +643,7 @@ __device__ void rules_warp(const ObserveParams &P, RulesScratch<G> &s, const int
         if (i < n_legal) {
           const uint32_t mv = s.moves[i];
           const uint32_t flat = mv >> 17;
-          if (g_mask) atomicOr(&g_mask[flat >> 5], 1u << (flat & 31));
-          if (want_flats) s.list[LIST_FLAT + i] = (uint16_t)flat;
+          if (want_flats) s.flats[FLAT_FIRST + i] = (uint16_t)flat;
           if (want_lists || P.playout) {
             int rank = 0;
             for (int j = 0; j < n_legal; j += 4) {
@@ -669,40 +663,36 @@ __device__ void rules_warp(const ObserveParams &P, RulesScratch<G> &s, const int
     }
   }
 
-  // ---- the record of ones / in-place update of the dense tensors (FPC_FLAG_INCREMENTAL) ---------
-  if (P.lists) {
-    uint16_t *gl = P.lists + (size_t)g * LIST_STRIDE;
-    const int new_flats = P.list_flats ? n_legal : 0;
-    const int new_cells = P.list_cells ? (n_cells > LIST_MAX_CELLS ? LIST_MAX_CELLS : n_cells) : 0;
-    if (P.inc_planes || P.inc_mask) {
-      const int old_flats = gl[0], old_cells = gl[1];
-      if (P.inc_planes) {
-        float *dst = P.inc_planes + (size_t)g * G::SSZ;
-        for (int i = lane; i < old_cells; i += 32) dst[gl[LIST_PLANES + i]] = 0.0f;
-      }
-      if (P.inc_mask) {
-        float *dst = P.inc_mask + (size_t)g * G::ASZ;
-        for (int i = lane; i < old_flats; i += 32) dst[gl[LIST_FLAT + i]] = 0.0f;
-      }
-      __syncwarp();  // warp-level memory ordering: every clear precedes every set (a cell may be in both lists)
-      if (P.inc_planes) {
-        float *dst = P.inc_planes + (size_t)g * G::SSZ;
-        for (int i = lane; i < new_cells; i += 32) dst[s.list[LIST_PLANES + i]] = 1.0f;
-      }
-      if (P.inc_mask) {
-        float *dst = P.inc_mask + (size_t)g * G::ASZ;
-        for (int i = lane; i < new_flats; i += 32) dst[s.list[LIST_FLAT + i]] = 1.0f;
-      }
+  // ---- the records of ones / in-place update of the dense tensors (FPC_FLAG_INCREMENTAL) ---------
+  if (P.cells || P.flats) {
+    uint16_t *gc = P.cells ? P.cells + (size_t)g * CELL_STRIDE : nullptr;
+    uint16_t *gf = P.flats ? P.flats + (size_t)g * FLAT_STRIDE : nullptr;
+    const int new_cells = n_cells > CELL_MAX ? CELL_MAX : n_cells, new_flats = n_legal;
+    if (P.inc_planes && gc) {
+      float *dst = P.inc_planes + (size_t)g * G::SSZ;
+      const int old = gc[0];
+      for (int i = lane; i < old; i += 32) dst[gc[CELL_FIRST + i]] = 0.0f;
     }
-    if (lane == 0) {
-      s.list[0] = (uint16_t)new_flats;
-      s.list[1] = (uint16_t)new_cells;
+    if (P.inc_mask && gf) {
+      float *dst = P.inc_mask + (size_t)g * G::ASZ;
+      const int old = gf[0];
+      for (int i = lane; i < old; i += 32) dst[gf[FLAT_FIRST + i]] = 0.0f;
     }
-    __syncwarp();
-    // only the used part of the record travels: header + plane cells, then the flat indices
-    const int used_a = (LIST_PLANES + new_cells + 7) / 8, first_b = LIST_FLAT / 8, used_b = (LIST_FLAT + new_flats + 7) / 8;
-    for (int i = lane; i < used_a; i += 32) reinterpret_cast<uint4 *>(gl)[i] = reinterpret_cast<const uint4 *>(s.list)[i];
-    for (int i = first_b + lane; i < used_b; i += 32) reinterpret_cast<uint4 *>(gl)[i] = reinterpret_cast<const uint4 *>(s.list)[i];
+    if (lane == 0) s.cells[0] = (uint16_t)new_cells, s.flats[0] = (uint16_t)new_flats;
+    __syncwarp();  // warp-level memory ordering: every clear precedes every set (a cell may be in both records)
+    if (P.inc_planes && gc) {
+      float *dst = P.inc_planes + (size_t)g * G::SSZ;
+      for (int i = lane; i < new_cells; i += 32) dst[s.cells[CELL_FIRST + i]] = 1.0f;
+    }
+    if (P.inc_mask && gf) {
+      float *dst = P.inc_mask + (size_t)g * G::ASZ;
+      for (int i = lane; i < new_flats; i += 32) dst[s.flats[FLAT_FIRST + i]] = 1.0f;
+    }
+    // only the used part of a record travels
+    if (gc)
+      for (int i = lane; i < (CELL_FIRST + new_cells + 7) / 8; i += 32) reinterpret_cast<uint4 *>(gc)[i] = reinterpret_cast<const uint4 *>(s.cells)[i];
+    if (gf)
+      for (int i = lane; i < (FLAT_FIRST + new_flats + 7) / 8; i += 32) reinterpret_cast<uint4 *>(gf)[i] = reinterpret_cast<const uint4 *>(s.flats)[i];
   }
 
   // ---- playout: play the chosen move or re-seed the slot ------------------------------------

@@ -40,7 +40,9 @@ class BatchedEnv:
         self.chosen = torch.zeros(self.n, dtype=torch.int64, device=self.device)
         self._planes = None
         self._mask = None
-        self._dense_known = set()  # output sets (planes?, mask?) this env has fully written at least once
+        # the handle that lets FPC_FLAG_INCREMENTAL update this env's own planes / mask buffers in place; it lives and
+        # dies with them (nothing is inferred from tensor addresses)
+        self._track = None
         self._moves = None
         self._flat = None
 
@@ -80,6 +82,30 @@ class BatchedEnv:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def track(self):
+        if self._track is None:
+            with torch.cuda.device(self.device):
+                self._track = self.L.fpc_dense_track_create(self.R, self.n)
+            if not self._track:
+                raise _lib.FpcError(self.L.fpc_last_error().decode())
+        return self._track
+
+    def invalidate_dense(self) -> None:
+        """Declare that something else wrote to planes_buffer() / mask_buffer(): the next incremental call rewrites them."""
+        if self._track is not None:
+            self.L.fpc_dense_track_invalidate(self._track)
+
+    def close(self) -> None:
+        if getattr(self, "_track", None):
+            self.L.fpc_dense_track_destroy(self._track)
+            self._track = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     # ---- state -------------------------------------------------------------------------------
     def load(self, records: np.ndarray | torch.Tensor) -> None:
         """Load board records: one [REC] record (broadcast to all games) or [n][REC]."""
@@ -109,12 +135,10 @@ class BatchedEnv:
                 k: int | torch.Tensor = -1, async_dense: bool = False, incremental: bool = False):
         """Legal moves / result / planes / mask of every game: rules_kernel, plus expand_kernel for the dense tensors
         (async_dense: do not wait for it, see join(); incremental: update the resident tensors in place)."""
-        incremental = incremental and (planes, mask) in self._dense_known  # fresh buffers: full rewrite first
-        self._dense_known.add((planes, mask))
         with torch.cuda.device(self.device):
             d_k = k if isinstance(k, torch.Tensor) else None
-            check(self.L.fpc_observe(
-                self.R, self.boards.data_ptr(), self.n,
+            check(self.L.fpc_observe_tracked(
+                self.track() if (planes or mask) else None, self.R, self.boards.data_ptr(), self.n,
                 _ptr(self.moves_buffer() if moves else None), _ptr(self.flat_buffer() if flat else None),
                 self.counts.data_ptr(), self.status.data_ptr(),
                 _ptr(self.planes_buffer() if planes else None), _ptr(d_k), -1 if d_k is not None else int(k),
@@ -125,9 +149,9 @@ class BatchedEnv:
     def encode(self, k: int | torch.Tensor = -1) -> torch.Tensor:
         with torch.cuda.device(self.device):
             d_k = k if isinstance(k, torch.Tensor) else None
-            check(self.L.fpc_encode(self.R, self.boards.data_ptr(), self.n, _ptr(d_k),
-                                    -1 if d_k is not None else int(k), self.planes_buffer().data_ptr(), 0,
-                                    self._stream()))
+            check(self.L.fpc_observe_tracked(self.track(), self.R, self.boards.data_ptr(), self.n, None, None, None, None,
+                                             self.planes_buffer().data_ptr(), _ptr(d_k),
+                                             -1 if d_k is not None else int(k), None, 0, self._stream()))
         return self._planes
 
     def make_moves(self, moves: torch.Tensor) -> torch.Tensor:
@@ -155,11 +179,9 @@ class BatchedEnv:
                      async_dense: bool = False, incremental: bool = False) -> None:
         """One ply for every game slot (BASELINE.json configs[1]); finished slots are re-seeded."""
         stride = self.n if game_stride is None else game_stride
-        incremental = incremental and (planes, mask) in self._dense_known
-        self._dense_known.add((planes, mask))
         with torch.cuda.device(self.device):
-            check(self.L.fpc_playout_step(
-                self.R, self.boards.data_ptr(), self.n, seed, self.game.data_ptr(), self.ply.data_ptr(),
+            check(self.L.fpc_playout_step_tracked(
+                self.track() if (planes or mask) else None, self.R, self.boards.data_ptr(), self.n, seed, self.game.data_ptr(), self.ply.data_ptr(),
                 self.start.data_ptr(), max_plies, stride, _ptr(self.chosen if chosen else None),
                 self.counts.data_ptr(), self.status.data_ptr(),
                 _ptr(self.planes_buffer() if planes else None), None, int(k),

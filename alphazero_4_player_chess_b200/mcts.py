@@ -62,7 +62,10 @@ class BatchedMCTS:
         self.leaf_status = torch.zeros(n, **i32)
         self.k = torch.zeros(n, **i32)
         self.planes = torch.empty((n, NUM_STATE_CHANNELS, R, R), dtype=torch.float32, device=dev)
-        self._planes_known = False  # set by the first (full) encode into this instance's planes tensor
+        with torch.cuda.device(self.device):
+            self._track = self.L.fpc_dense_track_create(R, n)  # lets select() update self.planes in place
+        if not self._track:
+            raise _lib.FpcError(self.L.fpc_last_error().decode())
         d = TreeDesc()
         d.R, d.n_games, d.node_cap, d.board_cap, d.C = R, n, self.node_cap, self.board_cap, float(args["C"])
         for name in ("parent", "first_child", "n_children", "visits", "move_flat", "board_idx", "value_sum", "prior",
@@ -85,13 +88,22 @@ class BatchedMCTS:
     def select(self) -> torch.Tensor:
         """Node.ChooseLeaf for every live game; returns the encoded leaf batch [n,24,R,R]."""
         # the planes tensor is resident and only read by the network between selects: after the first full encode
-        # it is updated in place (FPC_FLAG_INCREMENTAL)
-        flags = _lib.FLAG_INCREMENTAL if self._planes_known else 0
+        # through this instance's handle it is updated in place (FPC_FLAG_INCREMENTAL)
         with torch.cuda.device(self.device):
-            check(self.L.fpc_tree_select(C.byref(self.desc), int(self.batch_rotation), self.planes.data_ptr(), flags,
-                                         self._stream()))
-        self._planes_known = True
+            check(self.L.fpc_tree_select(C.byref(self.desc), int(self.batch_rotation), self.planes.data_ptr(),
+                                         _lib.FLAG_INCREMENTAL, self._track, self._stream()))
         return self.planes
+
+    def close(self) -> None:
+        if getattr(self, "_track", None):
+            self.L.fpc_dense_track_destroy(self._track)
+            self._track = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def expand_backup(self, logits: torch.Tensor, values: torch.Tensor) -> None:
         logits = logits.to(torch.float32).contiguous()

@@ -83,7 +83,8 @@ int fpc_record_from_fen(int R, const char *fen, int honour_castling, uint8_t *h_
 
 /* ---- device-pointer batch operations ------------------------------------------------------ */
 
-/* Observation of a batch (rules_kernel, plus expand_kernel when a dense tensor is asked for).  d_planes / d_mask
+/* Observation of a batch (rules_kernel, plus expand_kernel when a dense tensor is asked for; FPC_FLAG_INCREMENTAL is
+ * ignored here -- it needs a handle, see fpc_observe_tracked).  d_planes / d_mask
  * must be 16-byte aligned.  For each of n board records:
  *   legal moves      = fpchess::Board::GetLegalMoves (src/cpp/board.cpp:94-118) over
  *                      chess::Board::GetPseudoLegalMoves2 (engine/board.cpp:846-889)
@@ -102,7 +103,7 @@ int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_
 
 /* Dense outputs and streams.  The compact results (moves, counts, status, boards) are written by
  * rules_kernel on `stream`.  The dense f32 planes / mask are written by expand_kernel on an
- * internal second stream as soon as the rules kernel has produced their bit sets; by default
+ * internal second stream as soon as the rules kernel has produced the records of their ones; by default
  * `stream` then waits for it, so everything is ordered on `stream` as usual.  With
  * FPC_FLAG_ASYNC_DENSE that wait is left out: the next call's rules kernel overlaps this call's
  * expansion (the HBM-bound part), and the caller orders a consumer of the dense tensors with
@@ -110,14 +111,34 @@ int fpc_observe(int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_
 #define FPC_FLAG_ASYNC_DENSE 1
 int fpc_join(void *stream);
 
-/* FPC_FLAG_INCREMENTAL: resident dense tensors updated in place.  The library records which cells every dense
- * call sets to 1.0 (per host thread and device, for the last few (d_planes, d_mask, n, R) output sets).  When a
- * call carries this flag and its output set is one whose content is recorded, the rules kernel clears the
- * previously set cells and sets the new ones -- some 120 scattered 4-byte stores per game instead of rewriting
- * 113 KB -- and no expansion runs.  The result is bit-identical to a full rewrite PROVIDED nothing else wrote
- * to the tensors since the previous call with the same output set; otherwise (or for an unknown output set) the
- * call silently does the full rewrite.  Everything is ordered on `stream`. */
+/* FPC_FLAG_INCREMENTAL: resident dense tensors updated in place.  A fpc_dense_track handle owns the record of the
+ * cells the latest dense call THROUGH IT set to 1.0 in one planes tensor and / or one mask tensor (created for a
+ * board size and batch size on the current device).  When a *_tracked call carries this flag and the handle knows
+ * the content of every tensor the call asks for, the rules kernel clears the previously set cells and sets the
+ * new ones -- some 120 scattered 4-byte stores per game instead of rewriting 113 KB -- and no expansion runs.
+ * The result is bit-identical to a full rewrite PROVIDED nothing else wrote to the tensors since the previous call
+ * through the handle; the caller declares any such write with fpc_dense_track_invalidate().  Otherwise (first use,
+ * another tensor pointer, after an invalidate, no handle) the call does the full rewrite.  Nothing is inferred from
+ * pointer identity alone: a handle only vouches for tensors it has itself written since it was created or
+ * invalidated, so a tensor freed and re-allocated at the same address must come with a new (or invalidated) handle.
+ * Calls through one handle must be issued on one stream, or ordered by the caller.  Everything is ordered on `stream`. */
 #define FPC_FLAG_INCREMENTAL 2
+typedef struct fpc_dense_track fpc_dense_track;
+fpc_dense_track *fpc_dense_track_create(int R, int n); /* NULL on failure (fpc_last_error) */
+void fpc_dense_track_invalidate(fpc_dense_track *track);
+void fpc_dense_track_destroy(fpc_dense_track *track);   /* waits for the device; NULL is allowed */
+/* fpc_observe / fpc_playout_step (below) with a handle; track == NULL is the plain call. */
+int fpc_observe_tracked(fpc_dense_track *track, int R, const uint8_t *d_boards, int n, uint64_t *d_moves, int32_t *d_flat,
+                        int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all, float *d_mask,
+                        int flags, void *stream);
+int fpc_playout_step_tracked(fpc_dense_track *track, int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d_game,
+                             int32_t *d_ply, const uint8_t *d_start, int max_plies, uint64_t game_stride, uint64_t *d_chosen,
+                             int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all,
+                             float *d_mask, uint64_t *d_counters, int flags, void *stream);
+
+/* Releases what the calling host thread holds on the current device (internal streams, events, record workspace),
+ * after waiting for its pending work.  The next dense call re-creates them. */
+int fpc_shutdown(void);
 
 /* Measurement hook: time every expand_kernel and (dense-path) rules_kernel launch with CUDA events on the
  * streams they run on (up to 4096 launches per enable).  fpc_profile_read waits for those streams and
@@ -206,9 +227,10 @@ int fpc_tree_reset(const fpc_tree *t, const uint8_t *d_root_boards, void *stream
  * materialise the leaf's board, run the rules kernel on the leaf batch (legal moves + GetGameResult)
  * and encode it into d_planes [n_games][24][R][R] (Board::GetEncodedStates).  batch_rotation != 0
  * reproduces the reference: every leaf is rotated by the colour of the first live leaf
- * (src/cpp/board.cpp:354-355); 0 rotates each leaf by its own side to move.  flags: FPC_FLAG_INCREMENTAL updates
- * d_planes in place (the network only reads it between two selects), see above. */
-int fpc_tree_select(const fpc_tree *t, int batch_rotation, float *d_planes, int flags, void *stream);
+ * (src/cpp/board.cpp:354-355; the first leaf that is not terminal, as mcts.py:18-26 drops those before encoding);
+ * 0 rotates each leaf by its own side to move.  flags + track (may be NULL): FPC_FLAG_INCREMENTAL updates d_planes
+ * in place (the network only reads it between two selects), see above. */
+int fpc_tree_select(const fpc_tree *t, int batch_rotation, float *d_planes, int flags, fpc_dense_track *track, void *stream);
 
 /* MCTS.step after the network (mcts.py:66-79) + MCTS.expand (mcts.py:82-89) for every game with a
  * leaf: terminal leaf -> Backpropagate(0 | -1) and drop the root (node.cpp:33-43); otherwise

@@ -28,13 +28,7 @@ extern "C" int emul_rules(int R, const ObserveParams *P) {
   }
   return -1;
 }
-extern "C" int emul_strides(int R, int *plane_stride, int *mask_stride, int *list_stride) {
-  *list_stride = LIST_STRIDE;
-  switch (R) {
-    case 14: *plane_stride = Geo<14, 3>::PLANE_STRIDE, *mask_stride = Geo<14, 3>::MASK_STRIDE; return 0;
-    case 13: *plane_stride = Geo<13, 3>::PLANE_STRIDE, *mask_stride = Geo<13, 3>::MASK_STRIDE; return 0;
-    case 10: *plane_stride = Geo<10, 2>::PLANE_STRIDE, *mask_stride = Geo<10, 2>::MASK_STRIDE; return 0;
-    case 8: *plane_stride = Geo<8, 2>::PLANE_STRIDE, *mask_stride = Geo<8, 2>::MASK_STRIDE; return 0;
-  }
-  return -1;
+extern "C" int emul_strides(int *cell_first, int *cell_stride, int *flat_first, int *flat_stride) {
+  *cell_first = CELL_FIRST, *cell_stride = CELL_STRIDE, *flat_first = FLAT_FIRST, *flat_stride = FLAT_STRIDE;
+  return 0;
 }

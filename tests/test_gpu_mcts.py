@@ -82,6 +82,40 @@ def test_whole_trees_match_the_oracle(name, R, n_games, sims, batch_rotation):
     print(f"{name} rot={batch_rotation}: {len(trees)} games, {int(n_nodes.sum())} nodes, {n_dropped} dropped roots")
 
 
+def test_batch_rotation_ignores_terminal_leaves():
+    """The reference encodes a leaf batch with the colour of states[0], and states holds only the leaves that are
+    NOT terminal (mcts.py:18-26).  Game 0 here stands two plies before the end of a decisive game, so its selected
+    leaf is terminal in many simulations while the games behind it (other sides to move) are not: the batch
+    rotation must come from the first expandable leaf."""
+    from alphazero_4_player_chess_b200.fen import start_record
+    from tests.util import SEED
+    R = 8
+    o = oracle_for(R)
+    start = start_record("EIGHT_SIMPLE")
+    near_end, others = [], []
+    for game in range(60):
+        p = o.playout(start, SEED, game, 200)
+        if p["result"][-1] in (1, 2) and p["n"] > 6:
+            near_end.append(p["recs"][p["n"] - 3])
+        others.append(p["recs"][min(5 + game % 3, p["n"] - 1)])
+    assert near_end
+    others = [r for r in others if o.game_result(r)[0] == 0 and r[R * R] != near_end[0][R * R]][:6]
+    roots = np.stack([near_end[0]] + others + near_end[1:3])
+    sims = 60
+    trees = oracle_search(o, FakeNet(R), roots, 3, sims, batch_rotation=True)
+    m = run_gpu(R, roots, sims, batch_rotation=True)
+    assert int(m.dropped[0].item()) == 1 or any(v > 1 for v in trees[0].visits[1:])
+    n_nodes = m.n_nodes.cpu().numpy()
+    visits, value_sum, move_flat = m.visits.cpu().numpy(), m.value_sum.cpu().numpy(), m.move_flat.cpu().numpy()
+    for gi, t in enumerate(trees):
+        nn = len(t.parent)
+        assert n_nodes[gi] == nn, gi
+        assert move_flat[gi, :nn].tolist() == t.move_flat
+        assert visits[gi, :nn].tolist() == t.visits
+        assert value_sum[gi, :nn].tolist() == t.value_sum
+    assert int(m.dropped.sum().item()) >= 1  # a root did reach a terminal leaf
+
+
 def test_promotion_moves_collapse_into_one_child():
     """the four promotion moves share one (plane, from) index, so they become ONE child, made with an
     index-built move that does not promote.  Hand-made 14x14 position: a red pawn one step from its promotion row."""

@@ -447,6 +447,76 @@ def test_incremental_dense_update_equals_full_rewrite(name, R, n):
     b.playout_step(seed=SEED, planes=True, mask=True)
     torch.cuda.synchronize()
     assert torch.equal(a.planes_buffer(), b.planes_buffer()) and torch.equal(a.mask_buffer(), b.mask_buffer())
+    # ... and so do calls that rewrite only ONE of the two tensors between incremental calls (encode(), a planes-only
+    # observe with another rotation, a mask-only observe): the record of each tensor is kept on its own
+    for variant in range(4):
+        if variant == 0:
+            a.encode(k=2)
+        elif variant == 1:
+            a.observe(planes=True, mask=False, k=1)
+        elif variant == 2:
+            a.observe(planes=False, mask=True)
+        else:
+            a.observe(planes=True, mask=False, k=3, incremental=True)
+        a.playout_step(seed=SEED, planes=True, mask=True, incremental=True)
+        b.playout_step(seed=SEED, planes=True, mask=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a.planes_buffer(), b.planes_buffer()), variant
+        assert torch.equal(a.mask_buffer(), b.mask_buffer()), variant
+    # a write the library did not make is declared with invalidate_dense(): the next call rewrites everything
+    a.planes_buffer().fill_(3.0)
+    a.mask_buffer().fill_(3.0)
+    a.invalidate_dense()
+    a.observe(planes=True, mask=True, incremental=True)
+    b.observe(planes=True, mask=True)
+    assert torch.equal(a.planes_buffer(), b.planes_buffer()) and torch.equal(a.mask_buffer(), b.mask_buffer())
+
+
+def test_incremental_never_trusts_a_reused_address():
+    """Tensors freed and re-allocated at the same address: the new owner's first FPC_FLAG_INCREMENTAL call must be a
+    full rewrite.  Content tracking lives in explicit fpc_dense_track handles, never in pointer identity; the plain
+    (handle-less) entry points ignore the flag altogether."""
+    R, n = 14, 300
+    start = start_record("STANDARD", castling=True)
+    ref = BatchedEnv(R, n)
+    ref.reset_playout(start)
+    ref.observe(planes=True, mask=True)
+    torch.cuda.synchronize()
+    want_p, want_m = ref.planes_buffer().clone(), ref.mask_buffer().clone()
+    ptrs = set()
+    for round_ in range(3):
+        env = BatchedEnv(R, n)
+        env.reset_playout(start)
+        for _ in range(3):
+            env.playout_step(seed=SEED, planes=True, mask=True, incremental=True)
+        torch.cuda.synchronize()
+        ptrs.add((env.planes_buffer().data_ptr(), env.mask_buffer().data_ptr()))
+        env.close()
+        del env  # torch's caching allocator hands the same blocks to the next BatchedEnv
+        env = BatchedEnv(R, n)
+        env.reset_playout(start)
+        env.planes_buffer().fill_(9.0)  # whatever the previous owner left, plus garbage
+        env.mask_buffer().fill_(9.0)
+        ptrs.add((env.planes_buffer().data_ptr(), env.mask_buffer().data_ptr()))
+        env.observe(planes=True, mask=True, incremental=True)
+        torch.cuda.synchronize()
+        assert torch.equal(env.planes_buffer(), want_p) and torch.equal(env.mask_buffer(), want_m), round_
+        # the handle-less C entry point with the flag set: a full rewrite as well
+        env.planes_buffer().fill_(5.0)
+        env.mask_buffer().fill_(5.0)
+        _lib.check(env.L.fpc_observe(R, env.boards.data_ptr(), n, None, None, env.counts.data_ptr(), env.status.data_ptr(),
+                                     env.planes_buffer().data_ptr(), None, -1, env.mask_buffer().data_ptr(),
+                                     _lib.FLAG_INCREMENTAL, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(env.planes_buffer(), want_p) and torch.equal(env.mask_buffer(), want_m), round_
+        env.close()
+        del env
+    assert len(ptrs) < 6  # the addresses were indeed reused at least once
+    # per-thread state can be dropped and comes back on demand
+    _lib.check(ref.L.fpc_shutdown())
+    ref.observe(planes=True, mask=True)
+    torch.cuda.synchronize()
+    assert torch.equal(ref.planes_buffer(), want_p) and torch.equal(ref.mask_buffer(), want_m)
 
 
 def test_million_position_playout_checksum():

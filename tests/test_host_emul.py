@@ -23,9 +23,8 @@ class Params(C.Structure):
     """struct fpc::ObserveParams (csrc/fpc_rules.cuh)."""
     _fields_ = [("boards_in", C.c_void_p), ("boards_out", C.c_void_p), ("n", C.c_int), ("need_movegen", C.c_int),
                 ("moves", C.c_void_p), ("flat", C.c_void_p), ("counts", C.c_void_p), ("status", C.c_void_p),
-                ("plane_bits", C.c_void_p), ("k", C.c_void_p), ("k_all", C.c_int), ("mask_bits", C.c_void_p),
-                ("lists", C.c_void_p), ("list_cells", C.c_int), ("list_flats", C.c_int), ("inc_planes", C.c_void_p),
-                ("inc_mask", C.c_void_p), ("playout", C.c_int), ("seed", C.c_uint64), ("game", C.c_void_p),
+                ("k", C.c_void_p), ("k_all", C.c_int), ("cells", C.c_void_p), ("flats", C.c_void_p),
+                ("inc_planes", C.c_void_p), ("inc_mask", C.c_void_p), ("playout", C.c_int), ("seed", C.c_uint64), ("game", C.c_void_p),
                 ("ply", C.c_void_p), ("start", C.c_void_p), ("max_plies", C.c_int), ("game_stride", C.c_uint64),
                 ("chosen", C.c_void_p), ("counters", C.c_void_p)]
 
@@ -49,24 +48,24 @@ class Harness:
 
     def __init__(self, L, R):
         self.L, self.R, self.g = L, R, GEOMETRIES[R]
-        ps, ms, ls = C.c_int(), C.c_int(), C.c_int()
-        assert L.emul_strides(R, C.byref(ps), C.byref(ms), C.byref(ls)) == 0
-        self.plane_stride, self.mask_stride, self.list_stride = ps.value, ms.value, ls.value
+        cf, cs, ff, fs = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        assert L.emul_strides(C.byref(cf), C.byref(cs), C.byref(ff), C.byref(fs)) == 0
+        self.cell_first, self.cell_stride, self.flat_first, self.flat_stride = cf.value, cs.value, ff.value, fs.value
 
     def observe(self, recs, k_all=-1, playout=None, dense=True):
         """playout: None or dict(seed, games, plies, start, max_plies)."""
         recs = np.ascontiguousarray(recs, dtype=np.uint8)
         n = len(recs)
         out = dict(moves=np.zeros((n, 300), np.uint64), flat=np.zeros((n, 300), np.int32), counts=np.zeros(n, np.int32),
-                   status=np.zeros(n, np.int32), plane_bits=np.full((n, self.plane_stride), 0xDEADBEEF, np.uint32),
-                   mask_bits=np.full((n, self.mask_stride), 0xDEADBEEF, np.uint32))
+                   status=np.zeros(n, np.int32), cells=np.full((n, self.cell_stride), 0xDEAD, np.uint16),
+                   flats=np.full((n, self.flat_stride), 0xDEAD, np.uint16))
         p = Params()
         p.boards_in = recs.ctypes.data
         p.n, p.need_movegen, p.k_all = n, 1, k_all
         for name in ("moves", "flat", "counts", "status"):
             setattr(p, name, out[name].ctypes.data)
         if dense:
-            p.plane_bits, p.mask_bits = out["plane_bits"].ctypes.data, out["mask_bits"].ctypes.data
+            p.cells, p.flats = out["cells"].ctypes.data, out["flats"].ctypes.data
         if playout is not None:
             out["boards"] = recs.copy()
             out["game"] = np.ascontiguousarray(playout["games"], dtype=np.uint64)
@@ -81,10 +80,12 @@ class Harness:
         assert self.L.emul_rules(self.R, C.byref(p)) == 0
         return out
 
-    def dense(self, bits, n_floats):
-        """bit set -> the 0/1 f32 tensor expand_kernel would write."""
-        b = np.unpackbits(np.ascontiguousarray(bits).view(np.uint8), axis=1, bitorder="little")
-        return b[:, :n_floats].astype(np.float32)
+    def dense(self, records, first, n_floats):
+        """records of ones -> the 0/1 f32 tensor expand_kernel would write (zero fill, then the ones)."""
+        out = np.zeros((len(records), n_floats), np.float32)
+        for i, rec in enumerate(records):
+            out[i, rec[first: first + int(rec[0])].astype(np.int64)] = 1.0
+        return out
 
 
 def check_positions(h, o, recs, k_all=-1):
@@ -112,12 +113,11 @@ def check_positions(h, o, recs, k_all=-1):
         n_check += in_check
     turns = recs[:, R * R].astype(np.int32)
     k = turns if k_all < 0 else np.full(len(recs), k_all, np.int32)
-    planes = h.dense(out["plane_bits"], g.state_space_size).reshape(-1, 24, R, R)
+    planes = h.dense(out["cells"], h.cell_first, g.state_space_size).reshape(-1, 24, R, R)
     assert np.array_equal(planes, o.encode(recs, k))
-    mask = h.dense(out["mask_bits"], g.action_space_size).reshape(-1, g.num_action_channels, R, R)
+    mask = h.dense(out["flats"], h.flat_first, g.action_space_size).reshape(-1, g.num_action_channels, R, R)
     assert np.array_equal(mask, o.mask(recs))
-    # padding words of the bit sets are written (zero), not left as they were
-    assert not (out["plane_bits"][:, (g.state_space_size + 31) // 32:] != 0).any()
+    assert (out["flats"][:, 0] == out["counts"]).all()
     return n_check
 
 
