@@ -49,12 +49,16 @@ __global__ void __launch_bounds__(WPB * 32) rules_kernel(const __grid_constant__
   rules_warp<G>(P, scratch[wib], g, lane);
 }
 
-// Records -> dense f32 (0.0 / 1.0).  One CTA per game: every thread streams zeros over the game's two tensors
-// (coalesced 16-byte st.global.cs, nothing to wait for: the stores do not depend on any load), the CTA synchronises,
-// and one thread per recorded one writes its 1.0f.  The records are read while the zeros are in flight; the ones land
-// in lines this CTA has just written, so they merge in L2 and HBM sees each line once.  ~12 instructions per 512-byte
-// store instruction: the kernel leaves the issue slots to the rules kernel it overlaps.  HBM-write bound.
-constexpr int EXPAND_THREADS = 448;
+// Records -> dense f32 (0.0 / 1.0).  A persistent kernel, ONE CTA per SM, each CTA taking every gridDim.x-th game:
+// the records of the game are requested first, then every thread streams zeros over the game's two tensors (coalesced
+// 16-byte st.global.cs, nothing to wait for: the stores do not depend on any load), the CTA synchronises, and one
+// thread per recorded one writes its 1.0f.  The ones land in lines this CTA has just written, so they merge in L2 and
+// HBM sees each line once.  ~10 instructions per 512-byte store instruction and only 12 warps per SM: measured on
+// B200 (tools/overlap_probe.py) a grid that floods the SMs with store warps streams a little faster alone
+// (69-71 us vs 73 us per 462 MB) but loses twice that when the rules kernel of the next step shares the SMs, because
+// every shared-memory / global access of the rules warps queues behind the stores in the load/store pipe.
+// HBM-write bound.
+constexpr int EXPAND_THREADS = 384;
 
 template <class G>
 __global__ void __launch_bounds__(EXPAND_THREADS)
@@ -66,113 +70,20 @@ __global__ void __launch_bounds__(EXPAND_THREADS)
   for (int game = blockIdx.x; game < n; game += gridDim.x) {
     const uint16_t *gc = planes ? cells + (size_t)game * CELL_STRIDE : nullptr;
     const uint16_t *gf = mask ? flats + (size_t)game * FLAT_STRIDE : nullptr;
+    // the records are requested first and travel while the zeros are written
     const int n_cells = gc ? gc[0] : 0, n_flats = gf ? gf[0] : 0;
+    const int my_cell = t < n_cells ? gc[CELL_FIRST + t] : -1;
+    const int my_flat = t < n_flats ? gf[FLAT_FIRST + t] : -1;
     float *pl = planes + (size_t)game * G::SSZ, *mk = mask + (size_t)game * G::ASZ;
     if (planes)
       for (int i = t; i < P4; i += T) __stcs(reinterpret_cast<float4 *>(pl) + i, zero);
     if (mask)
       for (int i = t; i < M4; i += T) __stcs(reinterpret_cast<float4 *>(mk) + i, zero);
-    int my_cell[1], my_flat[1];
-    my_cell[0] = t < n_cells ? gc[CELL_FIRST + t] : -1;
-    my_flat[0] = t < n_flats ? gf[FLAT_FIRST + t] : -1;
     __syncthreads();  // block-wide memory ordering: every zero precedes every one
-    if (my_cell[0] >= 0) pl[my_cell[0]] = 1.0f;
-    if (my_flat[0] >= 0) mk[my_flat[0]] = 1.0f;
+    if (my_cell >= 0) pl[my_cell] = 1.0f;
+    if (my_flat >= 0) mk[my_flat] = 1.0f;
     for (int i = t + T; i < n_cells; i += T) pl[gc[CELL_FIRST + i]] = 1.0f;
     for (int i = t + T; i < n_flats; i += T) mk[gf[FLAT_FIRST + i]] = 1.0f;
-    __syncthreads();  // the next game of this CTA must not start zeroing before ... (different game: no overlap) -- keeps warps together
-  }
-}
-
-// The same expansion with the zeros written by the TMA engine: one warp per CTA, a zero tile in shared memory, and per
-// game a handful of cp.async.bulk shared->global copies issued by one lane -- no store instructions through the
-// load/store pipe, next to no issue slots: the SM is left to the rules kernel that overlaps it.  The ones follow once
-// the bulk group has completed (cross-proxy fence between the async-proxy zeros and the generic-proxy ones).
-// V: 0 = wait + ones per game, 1 = no ones (timing only), 2 = two games in flight per CTA (wait_group 1)
-template <class G, int TILE, int V>
-__global__ void __launch_bounds__(32) expand_tma_kernel(const uint16_t *__restrict__ cells, float *__restrict__ planes,
-                                                        const uint16_t *__restrict__ flats, float *__restrict__ mask, int n) {
-  extern __shared__ __align__(128) uint8_t zbuf[];
-  const int lane = threadIdx.x;
-  for (int i = lane; i < TILE / 16; i += 32) reinterpret_cast<uint4 *>(zbuf)[i] = make_uint4(0, 0, 0, 0);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncwarp();
-  const uint32_t src = (uint32_t)__cvta_generic_to_shared(zbuf);
-  int pc[5], pf[10];
-  float *ppl = nullptr, *pmk = nullptr;
-  bool have_prev = false;
-  for (int game = blockIdx.x; game < n; game += gridDim.x) {
-    float *pl = planes ? planes + (size_t)game * G::SSZ : nullptr, *mk = mask ? mask + (size_t)game * G::ASZ : nullptr;
-    if (lane == 0) {
-      if (pl)
-        for (int off = 0; off < G::SSZ * 4; off += TILE) {
-          const uint32_t sz = G::SSZ * 4 - off < TILE ? G::SSZ * 4 - off : TILE;
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint8_t *>(pl) + off), "r"(src), "r"(sz) : "memory");
-        }
-      if (mk)
-        for (int off = 0; off < G::ASZ * 4; off += TILE) {
-          const uint32_t sz = G::ASZ * 4 - off < TILE ? G::ASZ * 4 - off : TILE;
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint8_t *>(mk) + off), "r"(src), "r"(sz) : "memory");
-        }
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-    if (V == 1) continue;
-    // the records travel while the zeros are written
-    const uint16_t *gc = pl ? cells + (size_t)game * CELL_STRIDE : nullptr;
-    const uint16_t *gf = mk ? flats + (size_t)game * FLAT_STRIDE : nullptr;
-    const int n_cells = gc ? gc[0] : 0, n_flats = gf ? gf[0] : 0;
-    int c[5], f[10];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) c[j] = lane + 32 * j < n_cells ? gc[CELL_FIRST + lane + 32 * j] : -1;
-#pragma unroll
-    for (int j = 0; j < 10; ++j) f[j] = lane + 32 * j < n_flats ? gf[FLAT_FIRST + lane + 32 * j] : -1;
-    if (V == 2) {
-      // complete the PREVIOUS game while this one's zeros are in flight
-      if (have_prev) {
-        if (lane == 0) {
-          asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 5; ++j)
-          if (pc[j] >= 0) ppl[pc[j]] = 1.0f;
-#pragma unroll
-        for (int j = 0; j < 10; ++j)
-          if (pf[j] >= 0) pmk[pf[j]] = 1.0f;
-      }
-#pragma unroll
-      for (int j = 0; j < 5; ++j) pc[j] = c[j];
-#pragma unroll
-      for (int j = 0; j < 10; ++j) pf[j] = f[j];
-      ppl = pl, pmk = mk, have_prev = true;
-      continue;
-    }
-    if (lane == 0) {
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 5; ++j)
-      if (c[j] >= 0) pl[c[j]] = 1.0f;
-#pragma unroll
-    for (int j = 0; j < 10; ++j)
-      if (f[j] >= 0) mk[f[j]] = 1.0f;
-  }
-  if (V == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  if (V == 2 && have_prev) {
-    if (lane == 0) {
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 5; ++j)
-      if (pc[j] >= 0) ppl[pc[j]] = 1.0f;
-#pragma unroll
-    for (int j = 0; j < 10; ++j)
-      if (pf[j] >= 0) pmk[pf[j]] = 1.0f;
   }
 }
 
@@ -478,27 +389,17 @@ static int launch_observe(ObserveParams p, DenseOut d, cudaStream_t st, F after_
   if (rc != FPC_OK) return rc;
   CK(cudaStreamWaitEvent(S->side, S->rules_done[b], 0));
   if (prof) CK(cudaEventRecord(S->prof_ev[2 * S->prof_n], S->side));
-  int threads = EXPAND_THREADS;
+  {
+    static thread_local int sms[MAX_DEVICES] = {0};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (!sms[dev]) CK(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    const int grid = p.n < sms[dev] ? p.n : sms[dev];
 #ifdef FPC_EXPERIMENT
-  if (xknob("FPC_X_ETHREADS")) threads = xknob("FPC_X_ETHREADS");
-  if (xknob("FPC_X_NOEXPAND")) threads = 0;
-  if (xknob("FPC_X_TMA")) {
-    const int per_sm = xknob("FPC_X_TMA");
-    const int grid = p.n < 148 * per_sm ? p.n : 148 * per_sm, v = xknob("FPC_X_TMAV"), tile = xknob("FPC_X_TILE");
-#define TMA_ARGS p.cells, d.planes, p.flats, d.mask, p.n
-    if (tile == 32) {
-      static bool attr = false;
-      if (!attr) cudaFuncSetAttribute(expand_tma_kernel<G, 32768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768), attr = true;
-      expand_tma_kernel<G, 32768, 2><<<grid, 32, 32768, S->side>>>(TMA_ARGS);
-    } else if (tile == 4) expand_tma_kernel<G, 4096, 2><<<grid, 32, 4096, S->side>>>(TMA_ARGS);
-    else if (v == 1) expand_tma_kernel<G, 16384, 1><<<grid, 32, 16384, S->side>>>(TMA_ARGS);
-    else if (v == 2) expand_tma_kernel<G, 16384, 2><<<grid, 32, 16384, S->side>>>(TMA_ARGS);
-    else expand_tma_kernel<G, 16384, 0><<<grid, 32, 16384, S->side>>>(TMA_ARGS);
-    threads = 0;
-  }
-  if (threads)
+    if (!xknob("FPC_X_NOEXPAND"))
 #endif
-  expand_kernel<G><<<p.n, threads, 0, S->side>>>(p.cells, d.planes, p.flats, d.mask, p.n);
+    expand_kernel<G><<<grid, EXPAND_THREADS, 0, S->side>>>(p.cells, d.planes, p.flats, d.mask, p.n);
+  }
   CK(cudaGetLastError());
   if (prof) CK(cudaEventRecord(S->prof_ev[2 * S->prof_n++ + 1], S->side));
   CK(cudaEventRecord(S->expand_done[b], S->side));

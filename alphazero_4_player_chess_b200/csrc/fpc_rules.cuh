@@ -125,29 +125,20 @@ __device__ __forceinline__ void nearest(uint32_t occ, int k, int &pl, int &ph) {
   pl = 31 - fpc_clz(occ & ((1u << k) - 1u));
 }
 
-// Which enemy non-sliders attack a square from neighbour slot nb: 0-7 the knight squares (engine/board.cpp:676-694,
-// all eight whatever invalid_area is), 8-15 the adjacent squares in direction nb-8 (kings :753-772; pawns :697-750:
-// RED attacks from SW / SE of the target, YELLOW from NW / NE, BLUE from NW / SW, GREEN from NE / SE).
-template <class G>
-__device__ __forceinline__ bool neighbour_attacks(const uint8_t *mb, int t, int nb, int enemy_team, int &sq) {
-  const int R1 = t >> 4, C1 = t & 15;
-  int nr, nc;
-  if (nb < 8) {
-    nr = R1 + kdrow(nb), nc = C1 + kdcol(nb);
-  } else {
-    const int d = qdelta(nb - 8);
-    const int ur = (d + 24) / 16 - 1;
-    nr = R1 + ur, nc = C1 + d - ur * 16;
-  }
-  if ((unsigned)nr > 15u || (unsigned)nc > 15u) return false;
-  sq = (nr << 4) | nc;
-  const uint32_t p = mb[sq];
-  if (!present(p) || team_of(p) != enemy_team) return false;
-  const int type = type_of(p);
-  if (nb < 8) return type == KNIGHT;
-  if (type == KING) return true;
-  if (type != PAWN) return false;
-  return ((0xA0820A28u >> (8 * color_of(p))) >> (nb - 8)) & 1u;
+// Enemy non-sliders around a square.  Neighbour slots: 0-7 the knight squares (engine/board.cpp:676-694, all eight
+// whatever invalid_area is), 8-15 the adjacent squares in plane-order direction nb-8 (kings :753-772; pawns :697-750:
+// RED attacks from SW / SE of the target, YELLOW from NW / NE, BLUE from NW / SW, GREEN from NE / SE).  A quarter is
+// four slots; their mailbox deltas travel as four signed bytes.  A knight jump from an edge square may leave the
+// mailbox (rows) or wrap into the wall column of the neighbouring row (columns): both read as WALL.
+__device__ __forceinline__ uint32_t quarter_deltas(int sub) {
+  // knights (dcol,drow) (-2,-1)(-2,1)(-1,-2)(-1,2) | (1,-2)(1,2)(2,-1)(2,1); adjacent N NW W SW | S SE E NE
+  return sub == 0 ? 0x1FDF0EEEu : (sub == 1 ? 0x12F221E1u : (sub == 2 ? 0x0FFFEFF0u : 0xF1011110u));
+}
+__device__ __forceinline__ int quarter_square(int t, uint32_t deltas, int j) { return t + (int)(int8_t)(deltas >> (8 * j)); }
+__device__ __forceinline__ bool neighbour_hit(uint32_t p, int sub, int j, int enemy_team) {
+  const uint32_t m = p & 0xBCu, side = 0x80u | ((uint32_t)enemy_team << 5);  // presence, team and type bits
+  if (sub < 2) return m == (side | (KNIGHT << 2));
+  return m == (side | (KING << 2)) || (m == side && ((0xA0820A28u >> (8 * color_of(p) + (sub - 2) * 4 + j)) & 1u));
 }
 
 // One quarter of "is square t attacked by the enemy team" (engine/board.cpp:606-787 GetAttackers2, limit 1): the
@@ -159,15 +150,19 @@ __device__ __forceinline__ bool attack_quarter(const RulesScratch<G> &s, int t, 
   const int e = line_entry(sub, t), k = line_pos(sub, t);
   uint32_t occ = s.tabA[e] & 0xffffu;
   const uint32_t es = s.tabB[e];
+  const uint32_t deltas = quarter_deltas(sub);
+  uint32_t nbp[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int sq = quarter_square(t, deltas, j);
+    nbp[j] = (unsigned)sq < 256u ? s.mb[sq] : WALL;
+  }
   if (sub == pline) occ = (occ & ~pclr) | pset;
   int pl, ph;
   nearest(occ, k, pl, ph);
   bool hit = ((es >> ph) | (es >> pl)) & 1u;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int sq;
-    hit |= neighbour_attacks<G>(s.mb, t, sub * 4 + j, enemy_team, sq);
-  }
+  for (int j = 0; j < 4; ++j) hit |= neighbour_hit(nbp[j], sub, j, enemy_team);
   return hit;
 }
 
@@ -195,7 +190,7 @@ __device__ __forceinline__ void restrict_run(const uint32_t *bits, int from, Run
 }
 
 // Moves of the mover's piece (square `from`, piece byte p) along line `line`: two runs (lo / hi side).
-// Sliders (engine/board.cpp:209-311), king steps (:313-341; `ksafe` bit d = neighbour in direction d is a legal
+// Sliders (engine/board.cpp:209-311), king steps (:313-341; `ksafe` bit 4*d = neighbour in direction d is a legal
 // destination), pawns (:47-177: push and double push along the forward line, captures on the two forward diagonals,
 // promotion on the colour's promotion line, no en passant), knights (:179-207: lines 0-3 carry jumps 2*line and
 // 2*line+1; |drow| < invalid_area only).
@@ -243,8 +238,8 @@ __device__ __forceinline__ void gen_runs(const RulesScratch<G> &s, int from, uin
       (side_hi ? cap_hi : cap_lo) = 1;
     }
   } else if (type == KING) {
-    move_lo = cap_lo = (ksafe >> dlo) & 1u;
-    move_hi = cap_hi = (ksafe >> dhi) & 1u;
+    move_lo = cap_lo = (ksafe >> (4 * dlo)) & 1u;
+    move_hi = cap_hi = (ksafe >> (4 * dhi)) & 1u;
   } else {
     const bool straight = line < 2;
     const bool ok = type == QUEEN || (type == ROOK ? straight : (type == BISHOP && !straight));
@@ -481,10 +476,11 @@ __device__ void rules_warp(const ObserveParams &P, RulesScratch<G> &s, const int
               }
             }
           }
+          const uint32_t deltas = quarter_deltas(lane);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            int sq = 0;
-            if (neighbour_attacks<G>(s.mb, king_sq, lane * 4 + j, enemy_team, sq)) {
+            const int sq = quarter_square(king_sq, deltas, j);
+            if ((unsigned)sq < 256u && neighbour_hit(s.mb[sq], lane, j, enemy_team)) {
               ++chk;
               atomicOr(&s.tbits[sq >> 5], 1u << (sq & 31));
             }
@@ -507,26 +503,23 @@ __device__ void rules_warp(const ObserveParams &P, RulesScratch<G> &s, const int
           hit = attack_quarter<G>(s, t, sub, enemy_team, kl, 1u << line_pos(kl, king_sq), 0u);
         }
         const unsigned hb = __ballot_sync(FULL, hit), cb = __ballot_sync(FULL, cand);
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (((cb >> (4 * q)) & 1u) && ((hb >> (4 * q)) & 15u) == 0) ksafe |= 1u << q;
+        ksafe = cb & ~(hb | (hb >> 1) | (hb >> 2) | (hb >> 3)) & 0x11111111u;  // bit 4*d: direction d is a legal king step
       }
       __syncwarp();  // pinbits / tbits complete
 
       // ---- generation: lane = (piece, line), two runs of moves each; written out with a warp prefix sum -----------
-      const int items = n_chk >= 2 ? 0 : np * 4;  // double check: only the king moves (handled below)
-      const int rounds_items = n_chk >= 2 ? 4 : items;
-      for (int base = 0; base < rounds_items; base += 32) {
+      if (n_chk >= 2) {  // double check: only the king moves
+        if (lane == 0) s.plist[0] = (uint16_t)(king_sq | (s.mb[king_sq] << 8));
+        np = 1;
+        __syncwarp();
+      }
+      const int items = np * 4;
+      constexpr uint32_t KEY_STEP = (uint32_t)(G::NSQ * 8) << 14;  // one plane further in the compact move
+      for (int base = 0; base < items; base += 32) {
         const int item = base + lane;
         Run2 lo{0, 0, 0, 0, 0}, hi{0, 0, 0, 0, 0};
         int from = 0;
-        if (n_chk >= 2) {
-          // only the king: its four lines
-          if (item < 4) {
-            from = king_sq;
-            gen_runs<G>(s, from, s.mb[from], item, ksafe, lo, hi);
-          }
-        } else if (item < items) {
+        if (item < items) {
           const uint32_t e = s.plist[item >> 2];
           from = e & 0xff;
           const uint32_t p = e >> 8;
@@ -560,17 +553,14 @@ __device__ void rules_warp(const ObserveParams &P, RulesScratch<G> &s, const int
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const Run2 &r = h ? hi : lo;
-            if (r.promo && r.cnt) {
-              const int to = from + r.delta;
-              takes_king |= to == ek1 || to == ek2;
-              for (int j = 0; j < 4; ++j) s.moves[at++] = pack_compact<G>(from, to, r.plane0, KNIGHT + j, 0);
-            } else {
-              for (int j = 0; j < r.cnt; ++j) {
-                const int to = from + r.delta * (r.first + 1 + j);
-                takes_king |= to == ek1 || to == ek2;
-                s.moves[at++] = pack_compact<G>(from, to, r.plane0 + r.first + j, NO_PIECE, 0);
-              }
-            }
+            if (r.cnt == 0) continue;
+            // the run's moves differ by a constant: one plane and one step further (promotions: the piece type)
+            const int to0 = from + r.delta * (r.first + 1);
+            uint32_t mv = pack_compact<G>(from, to0, r.plane0 + r.first, r.promo ? KNIGHT : NO_PIECE, 0);
+            const uint32_t inc = r.promo ? 1u << 14 : KEY_STEP + (uint32_t)r.delta;
+            const int last = r.promo ? to0 : to0 + r.delta * (r.cnt - 1);  // only the last square of a run can hold a piece
+            takes_king |= last == ek1 || last == ek2;
+            for (int j = 0; j < r.cnt; ++j, mv += inc) s.moves[at++] = mv;
           }
           n_moves += total;
         }
@@ -634,7 +624,29 @@ __device__ void rules_warp(const ObserveParams &P, RulesScratch<G> &s, const int
       pick = (uint32_t)(((mix64(P.seed, game_id, (uint64_t)ply) >> 32) * (uint64_t)n_legal) >> 32);
     const bool want_lists = P.moves || P.flat;
     const bool want_flats = P.flats != nullptr;
-    if (want_lists || P.playout || want_flats) {
+    if ((want_lists || P.playout || want_flats) && n_legal <= 32) {
+      // one move per lane: a 15-step bitonic network over the warp leaves lane i with the i-th smallest key
+      __syncwarp();
+      uint32_t mv = lane < n_legal ? s.moves[lane] : 0xffffffffu;
+      if (want_lists || P.playout) {
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t other = __shfl_xor_sync(FULL, mv, j);
+            const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+            mv = keep_min ? (mv < other ? mv : other) : (mv > other ? mv : other);
+          }
+      }
+      if (lane < n_legal) {
+        const uint32_t flat = mv >> 17;
+        if (want_flats) s.flats[FLAT_FIRST + lane] = (uint16_t)flat;
+        if (P.moves) P.moves[(size_t)g * MAX_MOVES + lane] = expand_move<G>(s.mb, s.rights, mv);
+        if (P.flat) P.flat[(size_t)g * MAX_MOVES + lane] = (int32_t)flat;
+        if ((uint32_t)lane == pick) chosen_mv = mv;
+      }
+      __syncwarp();
+    } else if (want_lists || P.playout || want_flats) {
       // pad to a multiple of four with keys above every real one: the rank loop compares four keys per load
       if (lane < 4) s.moves[n_legal + lane] = 0xffffffffu;
       __syncwarp();

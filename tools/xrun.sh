@@ -1,12 +1,6 @@
 export FPC_LIB_PATH=tools/libfpc_x.so
-P="python tools/overlap_probe.py 300 200"
-FPC_X_SKIPRULES=1 FPC_X_TMA=2 FPC_X_TMAV=1 $P
-FPC_X_SKIPRULES=1 FPC_X_TMA=1 FPC_X_TMAV=2 $P
-FPC_X_SKIPRULES=1 FPC_X_TMA=2 FPC_X_TMAV=2 $P
-FPC_X_SKIPRULES=1 FPC_X_TMA=2 FPC_X_TILE=32 $P
-FPC_X_SKIPRULES=1 FPC_X_TMA=2 FPC_X_TILE=4 $P
-FPC_X_TMA=1 FPC_X_TMAV=2 $P
-FPC_X_TMA=2 FPC_X_TMAV=2 $P
-FPC_X_TMA=1 FPC_X_TILE=32 $P
-FPC_X_TMA=1 FPC_X_TILE=4 $P
-FPC_X_TMA=1 FPC_X_TMAV=2 FPC_X_RWARPS=8 $P
+P="python tools/overlap_probe.py 300 600"
+for parts in 1 2 4 7; do
+FPC_X_PARTS=$parts $P
+FPC_X_PARTS=$parts FPC_X_SKIPRULES=1 $P
+done
