@@ -166,13 +166,21 @@ __global__ void __launch_bounds__(1024) tree_batch_k_kernel(const fpc_tree T) {
 }
 
 // mcts.py:66-79 + 82-89 and node.cpp:33-43,133-154, one CTA per game.
-constexpr int EXP_THREADS = 320;  // >= FPC_MAX_MOVES: one thread per legal move
+constexpr int EXP_THREADS = 256;  // 8 CTAs per SM: 1,024 games are one wave on 148 SMs
+constexpr int EXP_WARPS = EXP_THREADS / 32;
+
+// online soft-max statistics: running maximum m and sum s of exp(x - m)
+__device__ __forceinline__ void softmax_merge(float &m, float &s, float om, float os) {
+  const float nm = fmaxf(m, om);
+  s = (m == nm ? s : s * __expf(m - nm)) + (om == nm ? os : os * __expf(om - nm));
+  m = nm;
+}
 
 template <class G>
 __global__ void __launch_bounds__(EXP_THREADS) tree_expand_backup_kernel(const fpc_tree T, const float *logits, const float *values) {
-  __shared__ float red_m[EXP_THREADS / 32], red_s[EXP_THREADS / 32];
-  __shared__ double red_d[EXP_THREADS / 32];
-  __shared__ int red_i[EXP_THREADS / 32];
+  __shared__ float red_m[EXP_WARPS], red_s[EXP_WARPS];
+  __shared__ double red_d[EXP_WARPS];
+  __shared__ int red_i[EXP_WARPS];
   __shared__ float s_max, s_sum;
   __shared__ double s_msum;
   __shared__ int s_base;
@@ -189,36 +197,60 @@ __global__ void __launch_bounds__(EXP_THREADS) tree_expand_backup_kernel(const f
     if (tid == 0) T.dropped[g] = 1;
   } else {
     value = values[g];
-    // ---- softmax over the whole action space (mcts.py:67), online max / sum -----------------
     const float *lg = logits + (size_t)g * G::ASZ;
-    // two passes (the second one hits L2): loads are independent of the running max / sum, so many are in flight
+    // ---- the legal moves' own logits are requested first (scattered, ~20 of them) ---------------------
+    const int cnt = T.leaf_counts[g];
+    const int k = T.k[g] & 3;
+    constexpr int PER = (MAX_MOVES + EXP_THREADS - 1) / EXP_THREADS;
+    int flat[PER];
+    float lgt[PER];
+    bool first[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int i = tid + q * EXP_THREADS;
+      flat[q] = -1, lgt[q] = 0.0f, first[q] = false;
+      if (i < cnt) {
+        flat[q] = T.leaf_flat[(size_t)g * MAX_MOVES + i];
+        first[q] = i == 0 || T.leaf_flat[(size_t)g * MAX_MOVES + i - 1] != flat[q];  // promotions share an index
+        if (first[q]) {
+          // policy[plane][r][c] = rot90(net_out, -k)[plane][r][c]: one clockwise quarter turn reads out[i][j] = in[R-1-j][i]
+          const int plane = flat[q] / G::NSQ, sq = flat[q] - plane * G::NSQ;
+          int r = sq / G::R, c = sq - r * G::R;
+          for (int t = 0; t < k; ++t) {
+            const int nr = G::R - 1 - c;
+            c = r;
+            r = nr;
+          }
+          lgt[q] = __ldg(lg + plane * G::NSQ + r * G::R + c);
+        }
+      }
+    }
+    // ---- softmax over the whole action space (mcts.py:67): ONE streaming pass, online max / sum; four independent
+    //      16-byte loads per thread and iteration keep enough bytes in flight to stream at the HBM rate -------------
     float m = -CUDART_INF_F, s = 0.0f;
     const float4 *lg4 = reinterpret_cast<const float4 *>(lg);
-#pragma unroll 8
-    for (int i = tid; i < G::ASZ / 4; i += EXP_THREADS) {
-      const float4 v = __ldg(lg4 + i);
-      m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
-    if (lane == 0) red_m[warp] = m;
-    __syncthreads();
-    m = red_m[0];
-#pragma unroll
-    for (int w = 1; w < EXP_THREADS / 32; ++w) m = fmaxf(m, red_m[w]);
-    __syncthreads();
-#pragma unroll 8
-    for (int i = tid; i < G::ASZ / 4; i += EXP_THREADS) {
-      const float4 v = __ldg(lg4 + i);
-      s += (expf(v.x - m) + expf(v.y - m)) + (expf(v.z - m) + expf(v.w - m));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(FULL, m, o), os = __shfl_xor_sync(FULL, s, o);
-      const float nm = fmaxf(m, om);
-      s = (m == nm ? s : s * expf(m - nm)) + (om == nm ? os : os * expf(om - nm));
+    constexpr int N4 = G::ASZ / 4;
+    int i = tid;
+    for (; i + 3 * EXP_THREADS < N4; i += 4 * EXP_THREADS) {
+      const float4 a = __ldcs(lg4 + i), b = __ldcs(lg4 + i + EXP_THREADS), c = __ldcs(lg4 + i + 2 * EXP_THREADS),
+                   d = __ldcs(lg4 + i + 3 * EXP_THREADS);
+      const float mx = fmaxf(fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))),
+                             fmaxf(fmaxf(fmaxf(c.x, c.y), fmaxf(c.z, c.w)), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w))));
+      const float nm = fmaxf(m, mx);
+      s = s * __expf(m - nm) + ((__expf(a.x - nm) + __expf(a.y - nm)) + (__expf(a.z - nm) + __expf(a.w - nm))) +
+          ((__expf(b.x - nm) + __expf(b.y - nm)) + (__expf(b.z - nm) + __expf(b.w - nm))) +
+          ((__expf(c.x - nm) + __expf(c.y - nm)) + (__expf(c.z - nm) + __expf(c.w - nm))) +
+          ((__expf(d.x - nm) + __expf(d.y - nm)) + (__expf(d.z - nm) + __expf(d.w - nm)));
       m = nm;
     }
+    for (; i < N4; i += EXP_THREADS) {
+      const float4 a = __ldcs(lg4 + i);
+      const float nm = fmaxf(m, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+      s = s * __expf(m - nm) + ((__expf(a.x - nm) + __expf(a.y - nm)) + (__expf(a.z - nm) + __expf(a.w - nm)));
+      m = nm;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) softmax_merge(m, s, __shfl_xor_sync(FULL, m, o), __shfl_xor_sync(FULL, s, o));
     if (lane == 0) {
       red_m[warp] = m;
       red_s[warp] = s;
@@ -226,82 +258,85 @@ __global__ void __launch_bounds__(EXP_THREADS) tree_expand_backup_kernel(const f
     __syncthreads();
     if (tid == 0) {
       float M = red_m[0];
-      for (int w = 1; w < EXP_THREADS / 32; ++w) M = fmaxf(M, red_m[w]);
+      for (int w = 1; w < EXP_WARPS; ++w) M = fmaxf(M, red_m[w]);
       double S = 0.0;
-      for (int w = 0; w < EXP_THREADS / 32; ++w)
+      for (int w = 0; w < EXP_WARPS; ++w)
         if (red_s[w] > 0.0f) S += (double)red_s[w] * (double)expf(red_m[w] - M);
       s_max = M;
       s_sum = (float)S;
     }
     __syncthreads();
-    // ---- legal moves: un-rotate (board.cpp:257-263), mask, renormalise (mcts.py:69-76) -------
-    const int cnt = T.leaf_counts[g];
-    const int k = T.k[g] & 3;
-    int flat = -1;
-    float p = 0.0f;
-    bool first = false;
-    if (tid < cnt) {
-      flat = T.leaf_flat[(size_t)g * MAX_MOVES + tid];
-      first = tid == 0 || T.leaf_flat[(size_t)g * MAX_MOVES + tid - 1] != flat;  // promotions share an index
-      if (first) {
-        // policy[plane][r][c] = rot90(net_out, -k)[plane][r][c]: one clockwise quarter turn reads
-        // out[i][j] = in[R-1-j][i]
-        const int plane = flat / G::NSQ, sq = flat - plane * G::NSQ;
-        int r = sq / G::R, c = sq - r * G::R;
-        for (int t = 0; t < k; ++t) {
-          const int nr = G::R - 1 - c;
-          c = r;
-          r = nr;
-        }
-        p = expf(lg[plane * G::NSQ + r * G::R + c] - s_max) / s_sum;
-      }
+    // ---- legal moves: un-rotated above; mask, renormalise (mcts.py:69-76) ---------------------------------
+    float p[PER];
+    double psum = 0.0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      p[q] = first[q] ? expf(lgt[q] - s_max) / s_sum : 0.0f;
+      psum += (double)p[q];
     }
-    double psum = (double)p;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(FULL, psum, o);
     if (lane == 0) red_d[warp] = psum;
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;
-      for (int w = 0; w < EXP_THREADS / 32; ++w) t += red_d[w];
+      for (int w = 0; w < EXP_WARPS; ++w) t += red_d[w];
       s_msum = t;
     }
     __syncthreads();
-    const float prior = (float)((double)p / s_msum);
-    // ---- one child per non-zero prior, ascending flat index (mcts.py:83-87, node.cpp:79-98) ----
-    const bool make = first && prior != 0.0f;
-    const unsigned bal = __ballot_sync(FULL, make);
-    if (lane == 0) red_i[warp] = __popc(bal);
-    __syncthreads();
-    if (tid == 0) {
-      int tot = 0;
-      for (int w = 0; w < EXP_THREADS / 32; ++w) {
+    // ---- one child per non-zero prior, ascending flat index (mcts.py:83-87, node.cpp:79-98): move i = tid + q*THREADS,
+    //      so the children of slice q come after every child of slice q-1 -------------------------------------------
+    int base_q = 0;
+    bool capped = false;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const float prior = (float)((double)p[q] / s_msum);
+      const bool make = first[q] && prior != 0.0f;
+      const unsigned bal = __ballot_sync(FULL, make);
+      if (lane == 0) red_i[warp] = __popc(bal);
+      __syncthreads();
+      int before = 0, tot = 0;
+      for (int w = 0; w < EXP_WARPS; ++w) {
         const int c = red_i[w];
-        red_i[w] = tot;
+        if (w < warp) before += c;
         tot += c;
       }
-      int base = T.n_nodes[g];
-      if (base + tot > T.node_cap) {
-        T.error[g] |= ERR_NODE_CAP;
-        base = -1;
-      } else {
-        T.n_nodes[g] = base + tot;
-        T.first_child[slab + leaf] = base;
-        T.n_children[slab + leaf] = tot;
+      if (q == 0) {
+        // the total number of children is needed up front: count the later slices too
+        int all = tot;
+#pragma unroll
+        for (int q2 = 1; q2 < PER; ++q2) {
+          const float pr2 = (float)((double)p[q2] / s_msum);
+          all += __syncthreads_count(first[q2] && pr2 != 0.0f);
+        }
+        if (tid == 0) {
+          int base = T.n_nodes[g];
+          if (base + all > T.node_cap) {
+            T.error[g] |= ERR_NODE_CAP;
+            base = -1;
+          } else {
+            T.n_nodes[g] = base + all;
+            T.first_child[slab + leaf] = base;
+            T.n_children[slab + leaf] = all;
+          }
+          s_base = base;
+        }
+        __syncthreads();
+        capped = s_base < 0;
       }
-      s_base = base;
-    }
-    __syncthreads();
-    if (make && s_base >= 0) {
-      const size_t c = slab + s_base + red_i[warp] + __popc(bal & ((1u << lane) - 1u));
-      T.parent[c] = leaf;
-      T.first_child[c] = 0;
-      T.n_children[c] = 0;
-      T.visits[c] = 1;  // node.h:28
-      T.move_flat[c] = flat;
-      T.board_idx[c] = -1;
-      T.value_sum[c] = 0.0;
-      T.prior[c] = prior;
+      if (make && !capped) {
+        const size_t c = slab + s_base + base_q + before + __popc(bal & ((1u << lane) - 1u));
+        T.parent[c] = leaf;
+        T.first_child[c] = 0;
+        T.n_children[c] = 0;
+        T.visits[c] = 1;  // node.h:28
+        T.move_flat[c] = flat[q];
+        T.board_idx[c] = -1;
+        T.value_sum[c] = 0.0;
+        T.prior[c] = prior;
+      }
+      base_q += tot;
+      __syncthreads();
     }
   }
   // ---- Node::Backpropagate (node.cpp:133-142): +v at the leaf, sign flips at every ancestor ------

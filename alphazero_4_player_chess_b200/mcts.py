@@ -22,10 +22,12 @@ ERR_NODE_CAP, ERR_BOARD_CAP, ERR_NO_CHILD, ERR_MOVE = 1, 2, 4, 8
 
 class BatchedMCTS:
     def __init__(self, R: int, n_games: int, neural_net, args: dict, device: str | torch.device = "cuda",
-                 batch_rotation: bool = False, node_cap: int | None = None):
+                 batch_rotation: bool = False, node_cap: int | None = None, cuda_graph: bool = False):
         """args: the reference's dict (`alphazero.py:291-306`): uses "C" and "num_searches".
         batch_rotation=True reproduces the reference bit for bit (a whole leaf batch is rotated by the
-        colour of its first state); False rotates every leaf by its own side to move."""
+        colour of its first expandable state); False rotates every leaf by its own side to move.
+        cuda_graph=True captures one whole simulation (select -> network -> expand/backup) in a CUDA graph after
+        three eager ones and replays it: the ~70 launches of a simulation become one."""
         self.geom = GEOMETRIES[R]
         self.R, self.n = R, int(n_games)
         self.net = neural_net
@@ -34,6 +36,8 @@ class BatchedMCTS:
         if self.device.type != "cuda":
             raise _lib.FpcError("BatchedMCTS needs a CUDA device (there is no CPU fallback)")
         self.batch_rotation = bool(batch_rotation)
+        self.cuda_graph = bool(cuda_graph)
+        self._graph = None
         self.L = _lib.lib()
         sims = int(args["num_searches"])
         # a leaf adds at most FPC_MAX_MOVES children; the legal-move average is ~19-38 at 14x14
@@ -114,13 +118,43 @@ class BatchedMCTS:
                                                 self._stream()))
 
     # ---- MCTS.search (mcts.py:17-43) -------------------------------------------------------------
+    def simulate(self) -> None:
+        """One simulation for every live game (`MCTS.step` + `MCTS.expand`, mcts.py:59-89)."""
+        planes = self.select()
+        logits, value = self.net(planes)
+        self.expand_backup(logits, value)
+
     @torch.no_grad()
-    def search(self, root_boards: torch.Tensor) -> "BatchedMCTS":
+    def search(self, root_boards: torch.Tensor, record=None, check: bool = True) -> "BatchedMCTS":
+        """record: optional callable(sim, logits, value) called after every network forward (eager mode only), e.g.
+        to keep the outputs of some games for a replay on the CPU oracle.  check: raise on tree errors (arena full ...)
+        instead of leaving them in `self.error`."""
         self.reset(root_boards)
-        for _ in range(int(self.args["num_searches"])):
-            planes = self.select()
-            logits, value = self.net(planes)
-            self.expand_backup(logits, value)
+        sims = int(self.args["num_searches"])
+        done = 0
+        if self.cuda_graph and record is None:
+            # eager warm-up (the first select writes the planes in full; cuDNN / cuBLAS pick their kernels), then capture
+            while self._graph is None and done < min(3, sims):
+                self.simulate()
+                done += 1
+            if self._graph is None and done < sims:
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.simulate()
+                self._graph = g  # capturing runs nothing: the simulation count is unchanged
+            while done < sims:
+                self._graph.replay()
+                done += 1
+        else:
+            for sim in range(sims):
+                planes = self.select()
+                logits, value = self.net(planes)
+                if record is not None:
+                    record(sim, logits, value)
+                self.expand_backup(logits, value)
+        if check:
+            self.check_errors()
         return self
 
     # ---- results -----------------------------------------------------------------------------------

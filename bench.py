@@ -18,9 +18,15 @@ the rules of step t+1 (FPC_FLAG_ASYNC_DENSE); the timed region ends after fpc_jo
 `--impl reference` times the UNMODIFIED reference on the host cores over the same workload: `value` is its
 full path (rules engine + GetEncodedStates + legal mask through its own pybind module, oracle/_ref/binding_R14,
 one process per core); `engine_only` is its rules engine alone (oracle/_ref/libref_engine_R14.so, C++ threads).
-Extra objects on our line: roofline (expand_kernel timed per launch on its stream), rules_only, incremental_dense
-(resident tensors updated in place -- NOT the headline), perft (configs[0]), mcts (configs[3] sample), cpu_baseline.
-"""
+Extra objects on our line: roofline (expand_kernel timed per launch on its stream), rules_only, castling_off (the
+reference arm's start record), incremental_dense (resident tensors updated in place -- NOT the headline), perft
+(configs[0]), mcts (configs[3] at its stated size at N = 1, configs[4] per GPU at N > 1; fp32 = the reference's precision
+beside bf16), dropin (the pybind drop-in through the reference's own MCTS call sequence, beside the reference binding),
+cpu_baseline.
+
+Position mix: before anything is timed every slot is fast-forwarded (rules only, untimed) and re-seeded at a staggered
+ply, so that the resident games are spread over whole games (opening to 2,048-ply cap) the way SURVEY 8d config 2 asks;
+`stats` reports the mix that was timed (legal moves, in-check share, pieces, ply quartiles)."""
 from __future__ import annotations
 
 import argparse
@@ -41,6 +47,7 @@ MAX_PLIES = 2048
 SEED = 0x5EED
 DENSE_BYTES_PER_POSITION = 24 * 196 * 4 + 120 * 196 * 4  # f32 planes + mask = 112,896
 BYTES_PER_POSITION = 2 * 208 + DENSE_BYTES_PER_POSITION  # 113,312
+FAST_FORWARD = 2048  # untimed rules-only plies before the timed region (one whole game at the ply cap)
 METRIC = "legal positions/sec (movegen+make+encode)"
 UNIT = "positions/s"
 
@@ -55,6 +62,8 @@ def workload_config(n_gpus: int) -> dict:
         "l2": "each step writes 464 MB of planes+mask per GPU (> 126 MB L2), so stores drain to HBM; "
               "the 0.85 MB board store is the resident state by design",
         "algorithmic_bytes_per_position": BYTES_PER_POSITION,
+        "position_mix": f"slots fast-forwarded {FAST_FORWARD} rules-only plies (untimed) and re-seeded at staggered plies: "
+                        "the timed positions span whole games",
     }
 
 
@@ -192,10 +201,13 @@ def run_reference(args) -> None:
         full = dict(eng)
         kind_note = "rules engine only (binding not built): " + eng["sample"]
     value = full["value"]
-    sample = f"{args.steps} steps x {sample_games} of the {N_GAMES} resident games; {kind_note}"
+    sample = (f"{args.steps} steps x {sample_games} of the {N_GAMES} resident games, castling rights OFF (the reference's "
+              "Python API cannot pass rights to Board(): its Player type is unhashable, fen_parser.py drops them; our "
+              f"arm reports this start record as `castling_off`), games from the start position; {kind_note}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sample_games / value * 1e3,
+        "ms_per_step_note": f"per {sample_games}-game sample step, derived from the rate (one process per core, no common clock)",
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": full["cores"], "kind": "reference", "sample": sample},
@@ -226,6 +238,42 @@ def cpu_baseline_leg() -> dict:
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{n} playout positions through oracle/fpc_oracle.c, single thread, {dt:.1f} s"}
+
+
+def fast_forward(env, start, stride, torch, plies: int = FAST_FORWARD, chunk: int = 64) -> None:
+    """Untimed, independent of --warmup: play `plies` rules-only plies and re-seed slot i (fresh game id, start record)
+    when `plies * (i / n)` plies are left, so that afterwards slot i is about that many plies into a game: the resident
+    games are spread evenly over opening .. ply cap (games that end earlier re-seed themselves as usual)."""
+    n = env.n
+    left_at_reset = (torch.arange(n, device=env.device, dtype=torch.float64) * (plies / n)).long()
+    reset_step = plies - left_at_reset  # slot i is re-seeded right before this step
+    start_t = torch.as_tensor(start, dtype=torch.uint8, device=env.device)
+    for s0 in range(0, plies, chunk):
+        sel = (reset_step >= s0) & (reset_step < s0 + chunk) & (reset_step < plies)
+        if bool(sel.any()):
+            env.boards[sel] = start_t
+            env.ply[sel] = 0
+            env.game[sel] += stride
+        for _ in range(min(chunk, plies - s0)):
+            env.playout_step(seed=SEED, max_plies=MAX_PLIES, game_stride=stride, planes=False, mask=False, k=-1)
+    env.counters.zero_()
+
+
+def mix_stats(env, stride, torch, steps: int = 64) -> dict:
+    """The position mix of the resident games, sampled over `steps` untimed rules-only plies after the timed region
+    (SURVEY 8d expects about 18.6 legal moves, 3.2 % in check and 17 pieces for whole random playouts)."""
+    from alphazero_4_player_chess_b200 import _lib
+    nsq = env.R * env.R
+    legal = in_check = pieces = 0.0
+    ply = env.ply.clone().float()
+    for _ in range(steps):
+        pieces += float((env.boards[:, :nsq] & 0x80).ne(0).sum()) / env.n
+        env.playout_step(seed=SEED, max_plies=MAX_PLIES, game_stride=stride, planes=False, mask=False, k=-1)
+        legal += float(env.counts.float().mean())
+        in_check += float((env.status & _lib.STATUS_CHECK).ne(0).float().mean())
+    q = torch.quantile(ply, torch.tensor([0.0, 0.25, 0.5, 0.75, 1.0], device=ply.device))
+    return {"avg_legal_moves": legal / steps, "in_check_share": in_check / steps, "avg_pieces_on_board": pieces / steps,
+            "ply_min_q1_median_q3_max": [int(x) for x in q.tolist()], "sampled_plies": steps}
 
 
 def run_ours(args) -> None:
@@ -263,7 +311,7 @@ def run_ours(args) -> None:
         env.playout_step(seed=SEED, max_plies=MAX_PLIES, game_stride=stride, planes=True, mask=True, k=-1,
                          async_dense=True)
 
-    # a few hundred plies in, the position mix is representative (captures, checks, promotions)
+    fast_forward(env, start, stride, torch)  # untimed: the resident games now span whole games
     for _ in range(max(args.warmup, 3)):
         step()
     env.join()
@@ -313,6 +361,28 @@ def run_ours(args) -> None:
     barrier()
     inc_ms = i0.elapsed_time(i1) / args.steps
     env.counters.copy_(env_counters)
+    mix = mix_stats(env, stride, torch) if rank == 0 else None
+    env.counters.copy_(env_counters)
+    # the reference arm's start record (castling rights off, as the reference's Python path builds its boards): same
+    # step, same game count, a short timed run of its own
+    off_ms = None
+    if world == 1:
+        start_off = start_record("STANDARD", castling=False)
+        env.reset_playout(start_off, first_game=shard.first_game)
+        fast_forward(env, start_off, stride, torch)
+        for _ in range(3):
+            step()
+        env.join()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        c0.record()
+        for _ in range(args.steps):
+            step()
+        env.join()
+        c1.record()
+        barrier()
+        off_ms = c0.elapsed_time(c1) / args.steps
+        env.counters.copy_(env_counters)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     counters = env.counters.clone()
     if world > 1:
@@ -372,11 +442,13 @@ def run_ours(args) -> None:
         ex_avg_ms = ex_ms.value / max(ex_n.value, 1)
         achieved = N_GAMES * DENSE_BYTES_PER_POSITION / (ex_avg_ms * 1e-3) / 1e9 if ex_n.value else 0.0
         step_gbs = N_GAMES * BYTES_PER_POSITION / (per_gpu_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
         if os.path.exists(tp):
             try:
                 traffic = json.load(open(tp)).get("expand_kernel")
+                traffic_src = ("static: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                               "(profiles/traffic_bytes_per_launch.json), NOT measured in this run")
             except Exception:
                 traffic = None
         out = {
@@ -390,7 +462,8 @@ def run_ours(args) -> None:
                             "as the reference's device='cuda' does, their expansion overlapping the next step"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "kernel": "expand_kernel", "bytes_per_launch": N_GAMES * DENSE_BYTES_PER_POSITION,
                          "avg_launch_ms": ex_avg_ms, "launches_timed": ex_n.value,
                          "rules_kernel_avg_launch_ms": ru_ms.value / max(ex_n.value, 1),
@@ -409,12 +482,18 @@ def run_ours(args) -> None:
             "clocks": clocks,
             "stats": {"positions": positions, "finished_games": int(counters[1].item()),
                       "avg_legal_moves": float(counters[6].item()) / max(positions, 1),
-                      "move_buffer_overflows": int(counters[7].item())},
+                      "move_buffer_overflows": int(counters[7].item()), "position_mix_after_timed_region": mix},
         }
+        if off_ms is not None:
+            out["castling_off"] = {"value": N_GAMES / (off_ms * 1e-3), "unit": UNIT, "ms_per_step": off_ms,
+                                   "note": "the same step from the reference arm's start record (castling rights off, "
+                                           "as the reference's Python path builds its boards), same game count"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg()
         if world == 1 and not args.no_mcts:
             out["perft"] = perft_leg(local)
+        if world == 1 and not args.no_dropin:
+            out["dropin"] = dropin_leg()
     # configs[3] / configs[4]: batched PUCT search, every rank on its own shard of games (no cross-GPU traffic in the
     # search; one all_reduce of the per-rank rates for the report)
     mcts = None
@@ -423,12 +502,18 @@ def run_ours(args) -> None:
         torch.cuda.empty_cache()
         mcts = mcts_leg(rank, world, local)
         if world > 1:
-            t = torch.tensor([mcts["value"], mcts["tree_kernels_only"]["value"], float(mcts["nodes"])], dtype=torch.float64,
-                             device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            mcts["value"], mcts["tree_kernels_only"]["value"], mcts["nodes"] = float(t[0]), float(t[1]), int(t[2])
-            mcts["games"] = mcts["games"] * world
-            mcts["note"] = f"sum over {world} ranks, each searching its own {mcts['games'] // world} games"
+            keys = [k for k in ("fp32", "bf16") if k in mcts]
+            vals = []
+            for k in keys:
+                vals += [mcts[k]["value"], mcts[k]["tree_kernels_only"]["value"], float(mcts[k]["nodes"])]
+            t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)  # NCCL: per-rank rates summed, statistics only
+            for i, k in enumerate(keys):
+                mcts[k]["value"], mcts[k]["tree_kernels_only"]["value"] = float(t[3 * i]), float(t[3 * i + 1])
+                mcts[k]["nodes"] = int(t[3 * i + 2])
+            mcts["games"] = mcts["games_per_gpu"] * world
+            mcts["value"] = mcts["fp32"]["value"]
+            mcts["note"] = f"sum over {world} ranks, each searching its own {mcts['games_per_gpu']} games"
     if rank == 0:
         if mcts is not None:
             out["mcts"] = mcts
@@ -437,52 +522,113 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
-def mcts_leg(rank: int, world: int, local: int, n_games: int = 1024, sims: int = 48) -> dict:
-    """configs[3] (batched PUCT self-play search): n_games x sims simulations with a random-init ResNet
-    10 x 128 of the reference architecture in PyTorch (bf16).  A bounded sample of the 400-sim
-    search so that the default run stays short; sims/s is per simulation and does not depend on the count."""
+def mcts_leg(rank: int, world: int, local: int) -> dict:
+    """M2, batched PUCT self-play search with a random-init ResNet 10 x 128 of the reference architecture in PyTorch.
+    N = 1: configs[3] at its stated size, 1,024 games x 400 simulations.  N > 1: configs[4], 8,192 games per GPU x 800
+    simulations (bf16 in full; the fp32 line is a 100-simulation sample of the same search: the fp32 network alone
+    takes ~0.19 s per 8,192-leaf batch).  fp32 = the reference's precision (src/py/net.py under PyTorch defaults) and
+    the headline `value`; bf16 beside it.  One simulation is captured in a CUDA graph and replayed."""
     import torch
 
     from alphazero_4_player_chess_b200.fen import start_record
     from alphazero_4_player_chess_b200.mcts import BatchedMCTS
     from alphazero_4_player_chess_b200.net import InferenceNet, PolicyValueNet
 
-    torch.manual_seed(0)
-    net = InferenceNet(PolicyValueNet(R, 10, 128, device=f"cuda:{local}"))
-    m = BatchedMCTS(R, n_games, net, {"C": 3, "num_searches": sims}, device=f"cuda:{local}")
+    single = world == 1
+    n_games = 1024 if single else 8192
+    sims_full = 400 if single else 800
+    dev = f"cuda:{local}"
     roots = torch.from_numpy(start_record("STANDARD")).unsqueeze(0).repeat(n_games, 1)
-    m.args["num_searches"] = 4
-    m.search(roots)  # warm-up (cuDNN autotune, allocator)
-    m.args["num_searches"] = sims
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    m.search(roots)
-    e1.record()
-    torch.cuda.synchronize()
-    total_ms = e0.elapsed_time(e1)
-    m.check_errors()
-    # the tree kernels alone: same loop with the network replaced by fixed outputs
-    logits = torch.randn((n_games, m.geom.action_space_size), device=m.device)
-    values = torch.zeros(n_games, device=m.device)
-    m.reset(roots)
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(sims):
-        m.select()
-        m.expand_backup(logits, values)
-    t1.record()
-    torch.cuda.synchronize()
-    tree_ms = t0.elapsed_time(t1)
-    return {"metric": "MCTS sims/sec", "value": n_games * sims / (total_ms * 1e-3), "unit": "sims/s",
-            "games": n_games, "sims_per_search": sims, "ms_per_sim_batch": total_ms / sims,
-            "tree_kernels_only": {"value": n_games * sims / (tree_ms * 1e-3), "unit": "sims/s",
-                                  "ms_per_sim_batch": tree_ms / sims},
-            "network_share": max(0.0, 1.0 - tree_ms / total_ms),
-            "nodes": int(m.n_nodes.sum().item()),
-            "config": "configs[3]: batched PUCT, 14x14 STANDARD roots, C=3, random-init ResNet 10x128 (reference "
-                      "architecture incl. the 23,520^2 policy Linear) in PyTorch bf16; bounded sample of "
-                      "the 400-sim search"}
+    out = {"metric": "MCTS sims/sec", "unit": "sims/s", "games_per_gpu": n_games, "games": n_games,
+           "config": ("configs[3]: batched PUCT, 1,024 games x 400 simulations" if single else
+                      "configs[4]: sharded self-play, 8,192 games per GPU x 800 simulations (65,536 games on 8 GPUs)") +
+                     ", 14x14 STANDARD roots, C=3, random-init ResNet 10x128 (reference architecture incl. the 23,520^2 "
+                     "policy Linear) in PyTorch; one simulation = select -> network -> expand/backup, CUDA-graphed"}
+    for name, bf16 in (("fp32", False), ("bf16", True)):
+        sims = sims_full if (single or bf16) else 100
+        torch.manual_seed(0)
+        net = InferenceNet(PolicyValueNet(R, 10, 128, device=dev), bf16=bf16)
+        # arena: ~20 children per expansion from these roots (max seen 19.8 per simulation); 48 leaves a 2.4x margin and
+        # the search raises if a tree outgrows it
+        m = BatchedMCTS(R, n_games, net, {"C": 3, "num_searches": sims}, device=dev, cuda_graph=True,
+                        node_cap=1 + sims_full * 48)
+        m.board_cap = m.board_cap  # sims + 2 boards per game: one per simulation plus the root
+        m.args["num_searches"] = 6
+        m.search(roots)  # warm-up: cuDNN / cuBLAS heuristics, allocator, graph capture
+        m.args["num_searches"] = sims
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m.search(roots, check=False)
+        e1.record()
+        torch.cuda.synchronize()
+        total_ms = e0.elapsed_time(e1)
+        m.check_errors()
+        nodes = int(m.n_nodes.sum().item())
+        # the network alone on the same leaf batch, and the tree kernels alone (fixed network outputs)
+        x = m.planes
+        for _ in range(2):
+            net(x)
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10 if single else 4
+        n0.record()
+        for _ in range(reps):
+            net(x)
+        n1.record()
+        torch.cuda.synchronize()
+        net_ms = n0.elapsed_time(n1) / reps
+        logits = torch.randn((n_games, m.geom.action_space_size), device=m.device)
+        values = torch.zeros(n_games, device=m.device)
+        m.reset(roots)
+        tree_sims = min(sims, 100)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(tree_sims):
+            m.select()
+            m.expand_backup(logits, values)
+        t1.record()
+        torch.cuda.synchronize()
+        tree_ms = t0.elapsed_time(t1) / tree_sims
+        tree_bytes = sum(getattr(m, a).numel() * getattr(m, a).element_size() for a in
+                         ("parent", "first_child", "n_children", "visits", "move_flat", "board_idx", "value_sum", "prior",
+                          "boards", "leaf_boards", "leaf_flat", "planes"))
+        out[name] = {"value": n_games * sims / (total_ms * 1e-3), "unit": "sims/s", "sims_per_search": sims,
+                     "ms_per_sim_batch": total_ms / sims, "network_alone_ms_per_batch": net_ms,
+                     "network_share": min(1.0, net_ms / (total_ms / sims)),
+                     "tree_kernels_only": {"value": n_games / (tree_ms * 1e-3), "unit": "sims/s", "ms_per_sim_batch": tree_ms},
+                     "nodes": nodes, "max_nodes_per_game": int(m.n_nodes.max().item()), "node_cap": m.node_cap,
+                     "tree_bytes": tree_bytes, "precision": "fp32 (PyTorch defaults: the reference's)" if not bf16 else "bf16 weights + activations"}
+        if sims != sims_full:
+            out[name]["note"] = f"{sims}-simulation sample of the {sims_full}-simulation search"
+        m.close()
+        del m, net, logits, x
+        torch.cuda.empty_cache()
+    out["value"] = out["fp32"]["value"]
+    return out
+
+
+def dropin_leg() -> dict:
+    """The pybind drop-in (dropin/alphazero_cpp) through the reference's own per-object MCTS call sequence
+    (tests/test_gpu_dropin.py::drive_search = src/py/mcts.py:17-89), 100 games x 50 simulations at 14x14 with the
+    deterministic stand-in network, beside the unmodified reference binding (oracle/_ref/binding_R14) on the same box.
+    Each in its own process: both modules are called alphazero_cpp."""
+    out = {}
+    for which in ("ours", "ref"):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dropin_probe.py"), which, "100", "50"],
+                               capture_output=True, text=True, timeout=600)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith(which + ":")]
+            if r.returncode != 0 or not line:
+                out[which] = {"unavailable": (r.stderr or r.stdout)[-200:]}
+                continue
+            out[which] = {"value": float(line[-1].split("=")[1].split()[0]), "unit": "sims/s", "line": line[-1]}
+        except Exception as e:  # pragma: no cover
+            out[which] = {"unavailable": repr(e)}
+    if "value" in out.get("ours", {}) and "value" in out.get("ref", {}):
+        out["ours_over_reference"] = out["ours"]["value"] / out["ref"]["value"]
+    out["note"] = ("reference call pattern: per-root ChooseLeaf (GetGameResult), per-state GetLegalMoves, batched "
+                   "GetEncodedStates / ExpandNodes; reference = its CPU engine behind the same Python loop")
+    return out
 
 
 def perft_leg(local: int) -> dict:
@@ -520,6 +666,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mcts", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -75,10 +75,17 @@ class Tree:
             self.children[node].append(len(self.parent) - 1)
 
 
-def search(o: Oracle, net, root_recs, C: float, num_searches: int, batch_rotation: bool = True):
+def search(o: Oracle, net, root_recs, C: float, num_searches: int, batch_rotation: bool = True, replay=None,
+           prior_source=None, prior_rtol: float = 2e-6):
     """mcts.py:17-43.  batch_rotation=True reproduces the reference (the whole leaf batch is encoded and
     un-rotated by the colour of states[0], `board.cpp:354-355`, `mcts.py:69`); False rotates every leaf
-    by its own side to move (the native mode of the CUDA path)."""
+    by its own side to move (the native mode of the CUDA path).
+
+    Record / replay: replay(sim, game_indices) -> (logits [k, A*R*R], value [k, 1]) stands in for
+    the network with outputs recorded from another run, so that float noise of the network cannot leak into the
+    comparison.  prior_source [n_games][node_cap] f32 does the same for the f32 priors: the priors computed here
+    (torch softmax, op by op) must agree with the recorded ones within prior_rtol, and the recorded bit patterns are
+    the ones stored in the tree, so that everything downstream (selection, visit counts, value sums) compares exactly."""
     R, A = o.R, o.A
     off_turn = R * R
     trees = [Tree(o, C, r) for r in root_recs]
@@ -96,8 +103,10 @@ def search(o: Oracle, net, root_recs, C: float, num_searches: int, batch_rotatio
         recs = np.stack([trees[gi].rec[leaf] for gi, leaf in leaves])
         turns = recs[:, off_turn].astype(np.int32)
         k = np.full(len(leaves), turns[0], dtype=np.int32) if batch_rotation else turns
-        enc = torch.from_numpy(o.encode(recs, k))
-        logits, value = net(enc)
+        if replay is not None:
+            logits, value = replay(_, [gi for gi, _leaf in leaves])
+        else:
+            logits, value = net(torch.from_numpy(o.encode(recs, k)))
         flat_policy = torch.softmax(logits, dim=1)  # mcts.py:67
         pol = flat_policy.view(-1, A, R, R)
         if batch_rotation:
@@ -112,5 +121,11 @@ def search(o: Oracle, net, root_recs, C: float, num_searches: int, batch_rotatio
         flat = pol.reshape(len(leaves), -1)
         for i, (gi, leaf) in enumerate(leaves):  # mcts.py:82-89: nonzero() order = ascending flat index
             nz = torch.nonzero(flat[i]).view(-1)
-            trees[gi].expand(leaf, nz.tolist(), flat[i][nz].tolist())
+            probs = flat[i][nz].tolist()
+            if prior_source is not None:
+                first = len(trees[gi].parent)
+                rec = prior_source[gi][first: first + len(probs)]
+                np.testing.assert_allclose(rec, np.array(probs, dtype=np.float32), rtol=prior_rtol, atol=0)
+                probs = [float(x) for x in rec]
+            trees[gi].expand(leaf, nz.tolist(), probs)
     return trees

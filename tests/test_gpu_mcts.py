@@ -163,7 +163,74 @@ def test_action_probs_and_capacity_errors():
     assert np.allclose(g0[flat[0, :n].cpu().numpy()], want / want.sum())
     # a node arena that is too small is reported, not overrun
     small = BatchedMCTS(R, 4, FakeNet(R, device="cuda"), {"C": 3, "num_searches": 30}, node_cap=40)
-    small.search(torch.from_numpy(roots))
+    small.search(torch.from_numpy(roots), check=False)
     torch.cuda.synchronize()
     assert int(small.error.max().item()) & 1
     assert int(small.n_nodes.max().item()) <= 40
+
+
+def test_cuda_graph_search_equals_eager_search():
+    """One simulation captured in a CUDA graph and replayed gives the same trees as the eager loop."""
+    R, sims = 14, 40
+    roots = torch.from_numpy(np.ascontiguousarray(mixed_positions("STANDARD", 64)))
+    trees = []
+    for graph in (False, True):
+        m = BatchedMCTS(R, 64, FakeNet(R, device="cuda"), {"C": 3, "num_searches": sims}, cuda_graph=graph)
+        m.search(roots)
+        m.search(roots)  # the second search replays the captured graph from its first simulation on
+        torch.cuda.synchronize()
+        trees.append(m)
+    a, b = trees
+    assert b._graph is not None
+    assert torch.equal(a.n_nodes, b.n_nodes)
+    nn = int(a.n_nodes.max())
+    for name in ("parent", "move_flat", "visits", "value_sum", "prior", "first_child", "n_children"):
+        assert torch.equal(getattr(a, name)[:, :nn], getattr(b, name)[:, :nn]), name
+
+
+def test_configs3_search_replayed_on_the_oracle():
+    """BASELINE.json configs[3] at its stated size and the reference's precision: 1,024 games x 400 simulations with the
+    random-init ResNet 10 x 128 in fp32 (PyTorch defaults, as src/py/net.py runs).  The network outputs of a sample of
+    games are recorded and the same games are replayed on the CPU restatement of fpchess::Node / MCTS.search
+    (oracle/mcts_port.py) with those outputs: tree shapes, moves, visit counts and value sums must be identical
+    (record / replay so that float noise of the network does not leak into the comparison)."""
+    from alphazero_4_player_chess_b200.fen import start_record
+    from alphazero_4_player_chess_b200.net import InferenceNet, PolicyValueNet
+    R, n, sims = 14, 1024, 400
+    o = oracle_for(R)
+    torch.manual_seed(0)
+    net = InferenceNet(PolicyValueNet(R, 10, 128, device="cuda"), bf16=False)
+    pool = mixed_positions("STANDARD", 256)
+    roots = np.ascontiguousarray(np.concatenate([pool] * (n // len(pool)))[:n])
+    roots[::2] = start_record("STANDARD")  # half of the games search from the start position
+    sample = torch.tensor([0, 1, 2, 3, 101, 255, 256, 511, 640, 777, 901, 1023], device="cuda")
+    rec_logits, rec_values = [], []
+
+    def record(sim, logits, value):
+        rec_logits.append(logits[sample].cpu())
+        rec_values.append(value[sample].reshape(-1, 1).cpu())
+
+    m = BatchedMCTS(R, n, net, {"C": 3, "num_searches": sims})
+    m.search(torch.from_numpy(roots), record=record)
+    torch.cuda.synchronize()
+    assert int(m.visits[:, 0].min()) >= 1 and int((m.visits[:, 0] == sims + 1).sum()) > n // 2
+    idx = sample.cpu().numpy()
+    pos = {int(g): i for i, g in enumerate(idx)}
+
+    def replay(sim, games):
+        rows = [pos[int(idx[g])] for g in games]
+        return rec_logits[sim][rows], rec_values[sim][rows]
+
+    prior = m.prior[sample].cpu().numpy()
+    trees = oracle_search(o, None, roots[idx], 3, sims, batch_rotation=False, replay=replay, prior_source=prior)
+    n_nodes, visits = m.n_nodes[sample].cpu().numpy(), m.visits[sample].cpu().numpy()
+    move_flat, value_sum, parent = m.move_flat[sample].cpu().numpy(), m.value_sum[sample].cpu().numpy(), m.parent[sample].cpu().numpy()
+    for i, t in enumerate(trees):
+        nn = len(t.parent)
+        assert n_nodes[i] == nn, (i, n_nodes[i], nn)
+        assert parent[i, :nn].tolist() == t.parent
+        assert move_flat[i, :nn].tolist() == t.move_flat
+        assert visits[i, :nn].tolist() == t.visits  # the visit-count vectors, every node
+        assert value_sum[i, :nn].tolist() == t.value_sum
+    print(f"configs[3]: {n} games x {sims} sims, {int(m.n_nodes.sum())} nodes; {len(trees)} games replayed on the oracle, "
+          f"{sum(len(t.parent) for t in trees)} nodes identical")
