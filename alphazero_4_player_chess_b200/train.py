@@ -87,12 +87,21 @@ class Learner:
     # ---- train / validate (alphazero.py:181-258) ------------------------------------------------------
     def train(self) -> int:
         bs = int(self.args["batch_size"])
-        if len(self.train_buf) < bs:
+        # alphazero.py:185-186: one mini-batch per batch_size entries of the replay buffer.  Under DDP every rank must run
+        # the SAME number of steps (each backward is a collective): ranks play games of different lengths and split
+        # train / validation with their own draws, so the count is agreed on first -- the minimum over the ranks, and
+        # nobody trains while some rank has less than one batch.
+        n_steps = -(-len(self.train_buf) // bs) if len(self.train_buf) >= bs else 0
+        if self.ddp is not None:
+            t = torch.tensor([n_steps], dtype=torch.int64, device=self.train_buf.boards.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            n_steps = int(t.item())
+        if n_steps == 0:
             return 0
         net = self.ddp if self.ddp is not None else self.model
         self.model.train()
         steps = 0
-        for _ in range(0, len(self.train_buf), bs):
+        for _ in range(n_steps):
             planes, policy_t, value_t = self._batch(self.train_buf)
             loss, pl, vl = self._loss(net, planes, policy_t, value_t)
             self.opt.zero_grad(set_to_none=True)

@@ -57,8 +57,18 @@ def _worker(rank, world, port, q):
     args = {"batch_size": 16, "replay_buffer_capacity": 256, "validation_buffer_capacity": 64}
     learner = Learner(sp, model, opt, args)
     assert learner.ddp is not None
-    learner.store(sp.replay(200))  # different data on every rank
-    steps = learner.train()
+    learner.store(sp.replay(200 if rank == 0 else 90))  # different data AND a different amount of it on every rank
+    local_steps = -(-len(learner.train_buf) // 16)
+    steps = learner.train()  # must not hang: the ranks agree on the smaller step count first
+    counts = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([local_steps, steps]))
+    assert counts[0][1] == counts[1][1] == min(int(counts[0][0]), int(counts[1][0])), counts
+    assert int(counts[0][0]) != int(counts[1][0])
+    # a rank with less than one batch keeps everybody from training (no collective is left half-entered)
+    starved = Learner(StubSelfPlay(8, rank), model, opt, args)
+    starved.ddp = learner.ddp
+    starved.store(sp.replay(200 if rank == 0 else 4))
+    assert starved.train() == 0
     flat = torch.cat([p.detach().flatten() for p in model.parameters()])
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
