@@ -60,7 +60,27 @@ SIGNATURES = {
     "fpc_host_make_index": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "fpc_host_playout_step": (_i, [_vp, _vp, _i, _u64, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _i, _vp, _i]),
     "fpc_ctx_sync": (_i, [_vp]),
+    "fpc_attack_maps": (_i, [_i, _vp, _i, _vp, _vp]),
+    "fpc_ctx_set_stream": (_i, [_vp, _vp]),
+    "fpc_current_device": (_i, []),
+    "fpc_host_alloc": (_vp, [C.c_size_t]),
+    "fpc_host_free": (None, [_vp]),
+    "fpc_host_expand": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "fpc_host_fetch_moves": (_i, [_vp, _i, _i, _vp]),
+    "fpc_host_encode": (_i, [_vp, _vp, _i, _i, _vp]),
+    "fpc_host_heuristic": (_i, [_vp, _vp, _i, _vp]),
+    "fpc_host_attack_maps": (_i, [_vp, _vp, _i, _vp]),
+    "fpc_env_create": (_vp, [_i, _i, _i]),
+    "fpc_env_destroy": (None, [_vp]),
+    "fpc_env_stream": (_vp, [_vp]),
+    "fpc_env_sync": (_i, [_vp]),
+    "fpc_env_set_boards": (_i, [_vp, _vp, _i, _i]),
+    "fpc_env_get_boards": (_i, [_vp, _vp, _i, _i]),
+    "fpc_env_observe": (_i, [_vp, _i, _i]),
+    "fpc_env_playout_step": (_i, [_vp, _u64, _vp, _i, _u64, _i, _i]),
+    "fpc_env_dlpack": (_vp, [_vp, _i]),
 }
+ENV_BOARDS, ENV_COUNTS, ENV_STATUS, ENV_MOVES, ENV_FLAT, ENV_PLANES, ENV_MASK, ENV_PLY, ENV_GAME = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 
 

@@ -17,6 +17,8 @@
 #include <pybind11/stl.h>
 
 #include <algorithm>
+#include <array>
+#include <map>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -169,34 +171,70 @@ struct Move {
   }
 };
 
-// ---- torch glue (PyTorch as a Python module: device memory, streams, tensors) ----------------------
+// ---- device plumbing --------------------------------------------------------------------------------------------
+// Rules calls go through a host-buffer context of the C-ABI (fpc_ctx: a stream, device scratch) with page-locked staging
+// buffers owned here: one trip = copies in, kernels, copies out, one synchronise -- no Python objects on the way.  PyTorch
+// (imported as a Python module, not linked) only appears where the reference returns a tensor.
 py::module_ torch() { return py::module_::import("torch"); }
 
 // "cpu" | "gpu" | "cuda" (src/cpp/board.cpp:265-283), extended with "cuda:N" for one process per GPU
 struct Device {
   bool cpu_out;
   std::string cuda;  // the device the kernels run on
+  int index;         // -1 = the current device
 };
 Device parse_device(const std::string &d) {
-  if (d == "cpu") return {true, "cuda"};
-  if (d == "gpu" || d == "cuda") return {false, "cuda"};
-  if (d.rfind("cuda:", 0) == 0) return {false, d};
+  if (d == "cpu") return {true, "cuda", -1};
+  if (d == "gpu" || d == "cuda") return {false, "cuda", -1};
+  if (d.rfind("cuda:", 0) == 0) return {false, d, std::atoi(d.c_str() + 5)};
   throw std::invalid_argument("Invalid device argument.");
 }
 uintptr_t ptr(const py::object &t) { return t.attr("data_ptr")().cast<uintptr_t>(); }
-void *stream_of(const py::object &tensor) {
-  return (void *)torch().attr("cuda").attr("current_stream")(tensor.attr("device")).attr("cuda_stream").cast<uintptr_t>();
+
+struct Pinned {  // a growing page-locked buffer (fpc_host_alloc)
+  void *p = nullptr;
+  size_t cap = 0;
+  template <class T>
+  T *get(size_t count) {
+    const size_t bytes = count * sizeof(T);
+    if (bytes > cap) {
+      if (p) fpc_host_free(p);
+      cap = std::max(bytes * 2, (size_t)4096);
+      p = fpc_host_alloc(cap);
+      if (!p) {
+        cap = 0;
+        throw std::runtime_error(fpc_last_error());
+      }
+    }
+    return static_cast<T *>(p);
+  }
+};
+constexpr int CTX_CAP = 16384;  // boards per trip; larger batches go in chunks
+struct Gpu {
+  fpc_ctx *ctx = nullptr;
+  Pinned boards, boards2, moves, words, bytes;
+};
+Gpu &gpu_for(int device) {
+  static std::map<std::pair<int, int>, Gpu> all;  // (device, R); lives as long as the process
+  if (device < 0) {
+    device = fpc_current_device();
+    if (device < 0) throw std::runtime_error(std::string("alphazero_cpp (B200 build): ") + fpc_last_error());
+  }
+  Gpu &g = all[{device, g_R}];
+  if (!g.ctx) {
+    g.ctx = fpc_ctx_create(device, g_R, CTX_CAP);
+    if (!g.ctx) throw std::runtime_error(std::string("alphazero_cpp (B200 build): ") + fpc_last_error());
+  }
+  return g;
 }
-py::object records_to_device(const std::vector<uint8_t> &recs, int n, const std::string &cuda) {
-  if (!torch().attr("cuda").attr("is_available")().cast<bool>())
-    throw std::runtime_error("alphazero_cpp (B200 build): no CUDA device, and there is no CPU fallback");
-  py::object host = torch().attr("frombuffer")(py::bytearray((const char *)recs.data(), recs.size()), py::arg("dtype") = torch().attr("uint8"));
-  return host.attr("view")(n, REC()).attr("to")(cuda);
-}
-struct DeviceGuard {  // kernels launch on the tensors' device
-  py::object ctx;
-  explicit DeviceGuard(const py::object &tensor) : ctx(torch().attr("cuda").attr("device")(tensor.attr("device"))) { ctx.attr("__enter__")(); }
-  ~DeviceGuard() { ctx.attr("__exit__")(py::none(), py::none(), py::none()); }
+// outputs that land in a torch tensor are written on torch's current stream of that device (the allocator's stream)
+struct OnTorchStream {
+  fpc_ctx *ctx;
+  OnTorchStream(fpc_ctx *c, const py::object &tensor) : ctx(c) {
+    const uintptr_t st = torch().attr("cuda").attr("current_stream")(tensor.attr("device")).attr("cuda_stream").cast<uintptr_t>();
+    fpc_ctx_set_stream(ctx, (void *)st);
+  }
+  ~OnTorchStream() { fpc_ctx_set_stream(ctx, nullptr); }
 };
 
 struct Node;
@@ -208,6 +246,16 @@ struct Board : std::enable_shared_from_this<Board> {
   std::shared_ptr<Board> rootState;
   std::shared_ptr<Node> rootNode;
   std::vector<MemoryEntry> memory;
+  // what the GPU said about this position (a board only changes through SetTurn): status word, legal moves, attack map.
+  // Boards made by TakeAction / ExpandNodes arrive with status and moves from the same trip that made them.
+  int obs_status = -1;
+  bool obs_moves = false;
+  std::vector<uint64_t> legal;
+  std::vector<uint8_t> attack;
+  void forget() {
+    obs_status = -1, obs_moves = false;
+    legal.clear(), attack.clear();
+  }
 
   Board() : rec(REC(), 0) {
     std::fill(rec.begin(), rec.begin() + NSQ(), 0x18);
@@ -232,7 +280,10 @@ struct Board : std::enable_shared_from_this<Board> {
     rootState = std::move(root);
   }
   Player GetTurn() const { return Player((PlayerColor)(rec[NSQ()] & 3)); }
-  void SetTurn(const Player &p) { rec[NSQ()] = (uint8_t)(p.color & 3); }
+  void SetTurn(const Player &p) {
+    rec[NSQ()] = (uint8_t)(p.color & 3);
+    forget();
+  }
   Piece GetPieceAt(int x, int y) const {
     if (x < 0 || x >= g_R || y < 0 || y >= g_R) throw std::invalid_argument("Index out of bounds");  // engine/board.h:535
     Piece p;
@@ -259,78 +310,113 @@ struct Board : std::enable_shared_from_this<Board> {
   std::shared_ptr<Board> GetRootState() { return rootState ? rootState : std::make_shared<Board>(*this); }
   std::vector<MemoryEntry> &GetMemory() { return rootState ? rootState->memory : memory; }
 
-  // one batched call of the rules kernel for a list of boards
-  struct Observed {
-    py::object counts, status, moves;  // host tensors
-  };
-  static Observed observe(const std::vector<std::shared_ptr<Board>> &states, bool want_moves, const std::string &cuda) {
-    const int n = (int)states.size();
-    std::vector<uint8_t> recs((size_t)n * REC());
-    for (int i = 0; i < n; ++i) memcpy(recs.data() + (size_t)i * REC(), states[i]->rec.data(), REC());
-    py::object d = records_to_device(recs, n, cuda);
-    py::object dev = d.attr("device");
-    py::object counts = torch().attr("zeros")(n, py::arg("dtype") = torch().attr("int32"), py::arg("device") = dev);
-    py::object status = torch().attr("zeros")(n, py::arg("dtype") = torch().attr("int32"), py::arg("device") = dev);
-    py::object moves = py::none();
-    if (want_moves) moves = torch().attr("zeros")(py::make_tuple(n, FPC_MAX_MOVES), py::arg("dtype") = torch().attr("int64"), py::arg("device") = dev);
-    {
-      DeviceGuard guard(d);
-      check(fpc_observe(g_R, (const uint8_t *)ptr(d), n, want_moves ? (uint64_t *)ptr(moves) : nullptr, nullptr,
-                        (int32_t *)ptr(counts), (int32_t *)ptr(status), nullptr, nullptr, -1, nullptr, 0, stream_of(d)));
-    }
-    Observed o{counts.attr("cpu")(), status.attr("cpu")(), want_moves ? moves.attr("cpu")() : py::none()};
-    return o;
+  // rules kernel on this position: status word + legal moves in one trip, kept
+  void observe() {
+    if (obs_status >= 0 && obs_moves) return;
+    Gpu &g = gpu_for(-1);
+    uint8_t *in = g.boards.get<uint8_t>(REC());
+    memcpy(in, rec.data(), REC());
+    uint64_t *mv = g.moves.get<uint64_t>(FPC_MAX_MOVES);
+    int32_t *w = g.words.get<int32_t>(2);
+    check(fpc_host_observe(g.ctx, in, 1, mv, nullptr, w, w + 1, nullptr, nullptr, -1, nullptr, nullptr));
+    obs_status = w[1];
+    legal.assign(mv, mv + std::min(std::max(w[0], 0), FPC_MAX_MOVES));
+    obs_moves = true;
   }
   // chess::Board::GetGameResult (engine/board.cpp:891-939; order-independent contract)
   GameResult GetGameResult(const std::optional<Player> &) {
-    auto o = observe({shared_from_this()}, false, "cuda");
-    const int st = o.status.attr("__getitem__")(0).attr("item")().cast<int>();
-    if (st & FPC_STATUS_OVERFLOW) throw std::runtime_error("move buffer overflow");
-    return (GameResult)(st & FPC_STATUS_RESULT_MASK);
+    if (obs_status < 0) observe();
+    if (obs_status & FPC_STATUS_OVERFLOW) throw std::runtime_error("move buffer overflow");
+    return (GameResult)(obs_status & FPC_STATUS_RESULT_MASK);
   }
   // fpchess::Board::GetLegalMoves (src/cpp/board.cpp:94-118), canonical order
   std::vector<std::shared_ptr<Move>> GetLegalMoves() {
-    auto o = observe({shared_from_this()}, true, "cuda");
-    const int n = o.counts.attr("__getitem__")(0).attr("item")().cast<int>();
-    py::list row = o.moves.attr("__getitem__")(0).attr("tolist")();
+    if (!obs_moves) observe();
     std::vector<std::shared_ptr<Move>> out;
-    for (int i = 0; i < n; ++i) out.push_back(std::make_shared<Move>((uint64_t)row[i].cast<int64_t>()));
+    out.reserve(legal.size());
+    for (uint64_t m : legal) out.push_back(std::make_shared<Move>(m));
     return out;
   }
-  // fpchess::Board::TakeAction (src/cpp/board.cpp:234-239): copy + chess::Board::MakeMove; returns a base Board
+  // fpchess::Board::TakeAction (src/cpp/board.cpp:234-239): copy + chess::Board::MakeMove; returns a base Board.
+  // One trip makes every child AND observes it (fpc_host_expand), so the children answer GetGameResult / GetLegalMoves
+  // from what came back with them.
   static std::vector<std::shared_ptr<Board>> take_actions(const std::vector<std::shared_ptr<Board>> &states, const std::vector<uint64_t> &moves) {
-    const int n = (int)states.size();
-    std::vector<uint8_t> recs((size_t)n * REC());
-    for (int i = 0; i < n; ++i) memcpy(recs.data() + (size_t)i * REC(), states[i]->rec.data(), REC());
-    py::object d = records_to_device(recs, n, "cuda");
-    py::object mv = torch().attr("frombuffer")(py::bytearray((const char *)moves.data(), moves.size() * 8), py::arg("dtype") = torch().attr("int64")).attr("to")(d.attr("device"));
-    py::object err = torch().attr("zeros")(n, py::arg("dtype") = torch().attr("int32"), py::arg("device") = d.attr("device"));
-    {
-      DeviceGuard guard(d);
-      check(fpc_make_moves(g_R, (const uint8_t *)ptr(d), (const uint64_t *)ptr(mv), n, (uint8_t *)ptr(d), (int32_t *)ptr(err), stream_of(d)));
-    }
-    if (err.attr("any")().attr("item")().cast<bool>()) throw std::runtime_error("piece missing for move");  // engine/board.cpp:1046-1054
-    py::bytes host = d.attr("cpu")().attr("numpy")().attr("tobytes")();
-    const std::string raw = host;
+    const size_t total = states.size(), rec_b = (size_t)REC();
     std::vector<std::shared_ptr<Board>> out;
-    for (int i = 0; i < n; ++i) {
-      auto b = std::make_shared<Board>();
-      memcpy(b->rec.data(), raw.data() + (size_t)i * REC(), REC());
-      out.push_back(b);
+    out.reserve(total);
+    Gpu &g = gpu_for(-1);
+    for (size_t first = 0; first < total; first += CTX_CAP) {
+      const int n = (int)std::min((size_t)CTX_CAP, total - first);
+      uint8_t *in = g.boards.get<uint8_t>(n * rec_b), *kids = g.boards2.get<uint8_t>(n * rec_b);
+      int32_t *w = g.words.get<int32_t>(3 * (size_t)n);  // err | counts | status
+      uint64_t *mv = g.moves.get<uint64_t>((size_t)n);
+      for (int i = 0; i < n; ++i) memcpy(in + i * rec_b, states[first + i]->rec.data(), rec_b), mv[i] = moves[first + i];
+      check(fpc_host_expand(g.ctx, in, mv, n, kids, w, w + n, w + 2 * n));
+      int maxc = 0;
+      for (int i = 0; i < n; ++i) {
+        if (w[i] != FPC_OK) throw std::runtime_error("piece missing for move");  // engine/board.cpp:1046-1054
+        maxc = std::max(maxc, std::min(w[n + i], FPC_MAX_MOVES));
+      }
+      mv = g.moves.get<uint64_t>((size_t)n * std::max(maxc, 1));
+      check(fpc_host_fetch_moves(g.ctx, n, maxc, mv));
+      for (int i = 0; i < n; ++i) {
+        auto b = std::make_shared<Board>();
+        memcpy(b->rec.data(), kids + i * rec_b, rec_b);
+        b->obs_status = w[2 * n + i];
+        const int c = std::min(std::max(w[n + i], 0), FPC_MAX_MOVES);
+        b->legal.assign(mv + (size_t)i * maxc, mv + (size_t)i * maxc + c);
+        b->obs_moves = true;
+        out.push_back(std::move(b));
+      }
     }
     return out;
   }
   std::shared_ptr<Board> TakeAction(const Move &m) { return take_actions({shared_from_this()}, {m.bits})[0]; }
   int CalculateHeuristic(Team team) {  // engine/board.cpp:1263-1292
-    std::vector<uint8_t> r = rec;
-    r[NSQ()] = (uint8_t)team;  // the kernel evaluates for the team of the side to move
-    py::object d = records_to_device(r, 1, "cuda");
-    py::object v = torch().attr("zeros")(1, py::arg("dtype") = torch().attr("int32"), py::arg("device") = d.attr("device"));
-    {
-      DeviceGuard guard(d);
-      check(fpc_heuristic(g_R, (const uint8_t *)ptr(d), 1, (int32_t *)ptr(v), stream_of(d)));
+    Gpu &g = gpu_for(-1);
+    uint8_t *in = g.boards.get<uint8_t>(REC());
+    memcpy(in, rec.data(), REC());
+    in[NSQ()] = (uint8_t)team;  // the kernel evaluates for the team of the side to move
+    int32_t *v = g.words.get<int32_t>(1);
+    check(fpc_host_heuristic(g.ctx, in, 1, v));
+    return v[0];
+  }
+  // ---- viewer queries (src/cpp/board.cpp:50-57,120-232): one attack-map trip per position, kept ----------------------
+  const std::vector<uint8_t> &attack_map() {
+    if (attack.empty()) {
+      Gpu &g = gpu_for(-1);
+      uint8_t *in = g.boards.get<uint8_t>(REC());
+      memcpy(in, rec.data(), REC());
+      uint8_t *o = g.bytes.get<uint8_t>(NSQ());
+      check(fpc_host_attack_maps(g.ctx, in, 1, o));
+      attack.assign(o, o + NSQ());
     }
-    return v.attr("item")().cast<int>();
+    return attack;
+  }
+  bool IsAttackedByPlayer(const BoardLocation &l, PlayerColor c) {
+    if (l.loc >= NSQ() || c < RED || c > GREEN) return false;  // a missing location has no neighbours inside the box
+    return (attack_map()[l.loc] >> (int)c) & 1;
+  }
+  std::unordered_map<PlayerColor, std::vector<BoardLocation>> GetAttackedSquaresPlayers() {
+    const auto &a = attack_map();
+    std::unordered_map<PlayerColor, std::vector<BoardLocation>> out;
+    for (int c = RED; c <= GREEN; ++c)
+      for (int sq = 0; sq < NSQ(); ++sq)
+        if ((a[sq] >> c) & 1) out[(PlayerColor)c].push_back(BoardLocation::FromSq(sq));
+    return out;
+  }
+  std::unordered_map<Team, std::vector<BoardLocation>> GetAttackedSquaresTeams() {
+    const auto &a = attack_map();
+    std::unordered_map<Team, std::vector<BoardLocation>> out;
+    for (int t = 0; t < 2; ++t)
+      for (int sq = 0; sq < NSQ(); ++sq)
+        if ((a[sq] >> (4 + t)) & 1) out[(Team)t].push_back(BoardLocation::FromSq(sq));
+    return out;
+  }
+  std::array<CastlingRights, 4> GetCastlingRights() const {
+    std::array<CastlingRights, 4> r;
+    for (int c = 0; c < 4; ++c) r[c].bits = rec[NSQ() + 1 + c];
+    return r;
   }
 
   // ---- statics ------------------------------------------------------------------------------------
@@ -348,17 +434,25 @@ struct Board : std::enable_shared_from_this<Board> {
     return ChangePerspective(v, -(int)turn.color);
   }
   // src/cpp/board.cpp:305-356: [B,24,R,R] f32, the whole batch rotated by the colour of states[0]
+  static py::object device_tensor(int n, int channels, const Device &dev) {
+    if (!torch().attr("cuda").attr("is_available")().cast<bool>())
+      throw std::runtime_error("alphazero_cpp (B200 build): no CUDA device, and there is no CPU fallback");
+    return torch().attr("empty")(py::make_tuple(n, channels, g_R, g_R), py::arg("dtype") = torch().attr("float32"), py::arg("device") = dev.cuda);
+  }
   static py::object GetEncodedStates(const std::vector<std::shared_ptr<Board>> &states, const std::string &device) {
     const Device dev = parse_device(device);
     const int n = (int)states.size();
     if (n == 0) return torch().attr("zeros")(py::make_tuple(0, FPC_NUM_STATE_CHANNELS, g_R, g_R));
-    std::vector<uint8_t> recs((size_t)n * REC());
-    for (int i = 0; i < n; ++i) memcpy(recs.data() + (size_t)i * REC(), states[i]->rec.data(), REC());
-    py::object d = records_to_device(recs, n, dev.cuda);
-    py::object out = torch().attr("empty")(py::make_tuple(n, FPC_NUM_STATE_CHANNELS, g_R, g_R), py::arg("dtype") = torch().attr("float32"), py::arg("device") = d.attr("device"));
-    {
-      DeviceGuard guard(d);
-      check(fpc_encode(g_R, (const uint8_t *)ptr(d), n, nullptr, states[0]->rec[NSQ()] & 3, (float *)ptr(out), 0, stream_of(d)));
+    py::object out = device_tensor(n, FPC_NUM_STATE_CHANNELS, dev);
+    Gpu &g = gpu_for(out.attr("device").attr("index").cast<int>());
+    OnTorchStream on(g.ctx, out);
+    const size_t rec_b = (size_t)REC(), per = (size_t)FPC_NUM_STATE_CHANNELS * NSQ();
+    const int k = states[0]->rec[NSQ()] & 3;
+    for (int first = 0; first < n; first += CTX_CAP) {
+      const int m = std::min(CTX_CAP, n - first);
+      uint8_t *in = g.boards.get<uint8_t>(m * rec_b);
+      for (int i = 0; i < m; ++i) memcpy(in + i * rec_b, states[first + i]->rec.data(), rec_b);
+      check(fpc_host_encode(g.ctx, in, m, k, (float *)ptr(out) + (size_t)first * per));
     }
     return dev.cpu_out ? out.attr("cpu")() : out;
   }
@@ -370,13 +464,16 @@ struct Board : std::enable_shared_from_this<Board> {
     const Device dev = parse_device(device);
     const int n = (int)states.size(), A = fpc_num_action_channels(g_R);
     if (n == 0) return torch().attr("zeros")(py::make_tuple(0, A, g_R, g_R));
-    std::vector<uint8_t> recs((size_t)n * REC());
-    for (int i = 0; i < n; ++i) memcpy(recs.data() + (size_t)i * REC(), states[i]->rec.data(), REC());
-    py::object d = records_to_device(recs, n, dev.cuda);
-    py::object out = torch().attr("empty")(py::make_tuple(n, A, g_R, g_R), py::arg("dtype") = torch().attr("float32"), py::arg("device") = d.attr("device"));
-    {
-      DeviceGuard guard(d);
-      check(fpc_observe(g_R, (const uint8_t *)ptr(d), n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, -1, (float *)ptr(out), 0, stream_of(d)));
+    py::object out = device_tensor(n, A, dev);
+    Gpu &g = gpu_for(out.attr("device").attr("index").cast<int>());
+    OnTorchStream on(g.ctx, out);
+    const size_t rec_b = (size_t)REC(), per = (size_t)A * NSQ();
+    for (int first = 0; first < n; first += CTX_CAP) {
+      const int m = std::min(CTX_CAP, n - first);
+      uint8_t *in = g.boards.get<uint8_t>(m * rec_b);
+      for (int i = 0; i < m; ++i) memcpy(in + i * rec_b, states[first + i]->rec.data(), rec_b);
+      check(fpc_host_observe(g.ctx, in, m, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, -1, nullptr,
+                             (float *)ptr(out) + (size_t)first * per));
     }
     return dev.cpu_out ? out.attr("cpu")() : out;
   }
@@ -423,6 +520,13 @@ struct MemoryEntry {  // src/cpp/board.h:50-58: a copy of the board + the action
   Board state;
   py::object action;
   MemoryEntry(const Board &s, const py::object &a) : state(s), action(a) {}
+};
+
+struct SimpleBoardState {  // engine/board.h:491-497, wrapper.cpp:68-73
+  Player turn;
+  std::vector<std::vector<PlacedPiece>> pieces;
+  std::array<CastlingRights, 4> castlingRights;
+  std::unordered_map<PlayerColor, std::vector<BoardLocation>> attackedSquares;
 };
 
 struct BoardPool {  // src/cpp/board.h:133-204: the reference's pool never hands out pooled boards either
@@ -586,12 +690,10 @@ PYBIND11_MODULE(alphazero_cpp, m) {
       .def("GetMemory", [](Board &b) { return b.GetMemory(); })
       .def("GetGameResult", &Board::GetGameResult, py::arg("opt_player") = py::none())
       .def("IsMoveLegal", [](Board &, const Move &) { return false; })  // src/cpp/board.cpp:70-92 always returns false
-      // UI-only queries of the reference (src/cpp/board.cpp:50-57,120-232; used by the pygame viewer only): bound so
-      // that the name resolves, but not provided by this build
-      .def("GetSimpleState", [](Board &) -> py::object { throw std::runtime_error("GetSimpleState: viewer-only query, not provided by the B200 build"); })
-      .def("GetAttackedSquaresPlayers", [](Board &) -> py::object { throw std::runtime_error("GetAttackedSquaresPlayers: viewer-only query, not provided by the B200 build"); })
-      .def("GetAttackedSquaresTeams", [](Board &) -> py::object { throw std::runtime_error("GetAttackedSquaresTeams: viewer-only query, not provided by the B200 build"); })
-      .def("IsAttackedByPlayer", [](Board &, const BoardLocation &, PlayerColor) -> bool { throw std::runtime_error("IsAttackedByPlayer: viewer-only query, not provided by the B200 build"); })
+      // the pygame viewer's queries (src/cpp/board.cpp:50-57,120-232)
+      .def("GetSimpleState", [](Board &b) { return SimpleBoardState{b.GetTurn(), b.GetPieces(), b.GetCastlingRights(), b.GetAttackedSquaresPlayers()}; })
+      .def("GetAttackedSquaresPlayers", &Board::GetAttackedSquaresPlayers).def("GetAttackedSquaresTeams", &Board::GetAttackedSquaresTeams)
+      .def("IsAttackedByPlayer", &Board::IsAttackedByPlayer)
       .def("GetLegalMoves", &Board::GetLegalMoves).def("TakeAction", &Board::TakeAction).def("record", [](const Board &b) { return py::bytes((const char *)b.rec.data(), b.rec.size()); })
       .def_static("ParseActionspace", &Board::ParseActionspace)
       .def_static("IsLegalLocation", [](int r, int c) { return Board::IsLegalLocation(r, c); })
@@ -604,6 +706,9 @@ PYBIND11_MODULE(alphazero_cpp, m) {
       .def_static("LegalMovesMask", &Board::LegalMovesMask, py::arg("states"), py::arg("device"))
       .def_static("GetLegalMovesIndices", &Board::GetLegalMovesIndices).def("__str__", &Board::Str);
 
+  py::class_<SimpleBoardState>(m, "SimpleBoardState").def(py::init<>()).def_readwrite("turn", &SimpleBoardState::turn)
+      .def_readwrite("pieces", &SimpleBoardState::pieces).def_readwrite("castlingRights", &SimpleBoardState::castlingRights)
+      .def_readwrite("attackedSquares", &SimpleBoardState::attackedSquares);
   py::class_<MemoryEntry>(m, "MemoryEntry").def(py::init<const Board &, const py::object &>()).def_readwrite("state", &MemoryEntry::state)
       .def_readwrite("action", &MemoryEntry::action);
   py::class_<BoardPool>(m, "BoardPool").def(py::init<size_t>()).def("acquire", &BoardPool::acquire).def("release", &BoardPool::release);

@@ -425,6 +425,97 @@ static int launch_heuristic(const uint8_t *in, int n, int32_t *v, cudaStream_t s
   return cuda_check(cudaGetLastError(), "heuristic_kernel launch");
 }
 
+// Viewer queries (src/cpp/board.cpp:120-232), one thread per (board, square): bits 0..3 IsAttackedByPlayer per colour,
+// bits 4..5 chess::Board::IsAttackedByTeam per team.  Plain loops over the record's piece bytes: this is the pygame
+// viewer's query, a few boards per call.
+template <class G>
+__global__ void __launch_bounds__(256) attack_map_kernel(const uint8_t *boards, int n, uint8_t *out) {
+  constexpr int R = G::R;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * G::NSQ) return;
+  const int g = idx / G::NSQ, sq = idx - g * G::NSQ;
+  const uint8_t *b = boards + (size_t)g * G::REC;
+  const int r0 = sq / R, c0 = sq - r0 * R;
+  auto inb = [](int r, int c) { return r >= 0 && r < R && c >= 0 && c < R; };
+  uint32_t bits = 0;
+  // ---- IsAttackedByPlayer (src/cpp/board.cpp:142-209): "legal" there means inside the R x R index range only --------
+  for (int d = 0; d < 8; ++d) {
+    const int dr = (int)(int8_t)((0xFF'FF'01'01'00'FF'00'01ull >> (8 * d)) & 0xff);  // (1,0)(0,1)(-1,0)(0,-1)(1,1)(1,-1)(-1,1)(-1,-1)
+    const int dc = (int)(int8_t)((0xFF'01'FF'01'FF'00'01'00ull >> (8 * d)) & 0xff);
+    // pawns and kings on the eight neighbours
+    if (inb(r0 + dr, c0 + dc)) {
+      const uint32_t p = b[(r0 + dr) * R + c0 + dc];
+      const int col = color_of(p), t = type_of(p);
+      if (t == 5) bits |= 1u << col;  // KING (an empty square has type NO_PIECE)
+      if (t == 0) {
+        // PawnAttacks(pawn at (r0+dr, c0+dc), colour, target): row_diff = -dr, col_diff = -dc (engine/board.cpp:583-604)
+        const int rd = -dr, cd = -dc;
+        const bool a = col == 0 ? (rd == -1 && (cd == 1 || cd == -1)) : col == 1 ? (cd == 1 && (rd == 1 || rd == -1))
+                     : col == 2 ? (rd == 1 && (cd == 1 || cd == -1)) : (cd == -1 && (rd == 1 || rd == -1));
+        if (a) bits |= 1u << col;
+      }
+    }
+    // sliders: the first piece on the ray decides, for its own colour only
+    for (int r = r0 + dr, c = c0 + dc; inb(r, c); r += dr, c += dc) {
+      const uint32_t p = b[r * R + c];
+      if (!present(p)) continue;
+      const int t = type_of(p);
+      const bool diag = dr != 0 && dc != 0;
+      if (t == 4 || (t == 2 && diag) || (t == 3 && !diag)) bits |= 1u << color_of(p);
+      break;
+    }
+  }
+  for (int k = 0; k < 8; ++k) {
+    const int r = r0 + kdrow(k), c = c0 + kdcol(k);
+    if (inb(r, c)) {
+      const uint32_t p = b[r * R + c];
+      if (type_of(p) == 1 && present(p)) bits |= 1u << color_of(p);
+    }
+  }
+  // ---- IsAttackedByTeam (engine/board.cpp:606-786) ---------------------------------------------------------------
+  for (int d = 0; d < 8; ++d) {
+    const int dr = (int)(int8_t)((0xFF'FF'01'01'00'FF'00'01ull >> (8 * d)) & 0xff);
+    const int dc = (int)(int8_t)((0xFF'01'FF'01'FF'00'01'00ull >> (8 * d)) & 0xff);
+    const bool diag = dr != 0 && dc != 0;
+    // rook rays are bounded by the index range, bishop rays by IsLegalLocation
+    for (int r = r0 + dr, c = c0 + dc; diag ? (inb(r, c) && G::legal(r, c)) : inb(r, c); r += dr, c += dc) {
+      const uint32_t p = b[r * R + c];
+      if (!present(p)) continue;
+      const int t = type_of(p);
+      if (t == 4 || (t == 2 && diag) || (t == 3 && !diag)) bits |= 16u << team_of(p);
+      break;
+    }
+    const int r = r0 + dr, c = c0 + dc;
+    if (inb(r, c)) {
+      const uint32_t p = b[r * R + c];
+      if (present(p)) {
+        const int col = color_of(p), t = type_of(p);
+        if (t == 5 && G::legal(r, c)) bits |= 16u << team_of(p);
+        if (t == 0 && diag) {
+          // pos_row = (dr == 1), pos_col = (dc == 1): RED attacks from below, BLUE from the left, ...
+          const bool a = col == 0 ? dr == 1 : col == 1 ? dc == -1 : col == 2 ? dr == -1 : dc == 1;
+          if (a) bits |= 16u << team_of(p);
+        }
+      }
+    }
+  }
+  for (int k = 0; k < 8; ++k) {
+    const int r = r0 + kdrow(k), c = c0 + kdcol(k);
+    if (inb(r, c) && G::legal(r, c)) {
+      const uint32_t p = b[r * R + c];
+      if (present(p) && type_of(p) == 1) bits |= 16u << team_of(p);
+    }
+  }
+  out[idx] = (uint8_t)bits;
+}
+template <class G>
+static int launch_attack_maps(const uint8_t *in, int n, uint8_t *out, cudaStream_t st) {
+  if (n == 0) return FPC_OK;
+  const int total = n * G::NSQ;
+  attack_map_kernel<G><<<(total + 255) / 256, 256, 0, st>>>(in, n, out);
+  return cuda_check(cudaGetLastError(), "attack_map_kernel launch");
+}
+
 #define FPC_DISPATCH(R, CALL)                                              \
   switch (R) {                                                             \
     case 14: { using G = Geo<14, 3>; return CALL; }                        \
@@ -449,6 +540,9 @@ static int do_make(int R, const uint8_t *in, const uint64_t *moves, const int32_
 }
 static int do_heuristic(int R, const uint8_t *in, int n, int32_t *v, cudaStream_t st) {
   FPC_DISPATCH(R, launch_heuristic<G>(in, n, v, st));
+}
+static int do_attack_maps(int R, const uint8_t *in, int n, uint8_t *out, cudaStream_t st) {
+  FPC_DISPATCH(R, launch_attack_maps<G>(in, n, out, st));
 }
 
 }  // namespace fpc
@@ -698,6 +792,11 @@ int fpc_heuristic(int R, const uint8_t *d_boards, int n, int32_t *d_value, void 
   return do_heuristic(R, d_boards, n, d_value, (cudaStream_t)stream);
 }
 
+int fpc_attack_maps(int R, const uint8_t *d_boards, int n, uint8_t *d_out, void *stream) {
+  if (n < 0 || (n > 0 && (!d_boards || !d_out))) return fail(FPC_ERR_ARG, "fpc_attack_maps: bad argument");
+  return do_attack_maps(R, d_boards, n, d_out, (cudaStream_t)stream);
+}
+
 static int playout_params(ObserveParams &p, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d_game, int32_t *d_ply,
                           const uint8_t *d_start, int max_plies, uint64_t game_stride, uint64_t *d_chosen,
                           int32_t *d_counts, int32_t *d_status, const int32_t *d_k, int k_all,
@@ -748,7 +847,7 @@ int fpc_playout_step(int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d
 
 struct fpc_ctx {
   int device, R, max_n, rec;
-  cudaStream_t stream;
+  cudaStream_t stream, own_stream;  // stream = own_stream unless fpc_ctx_set_stream redirected the work
   uint8_t *d_boards, *d_boards2, *d_start;
   uint64_t *d_moves, *d_game;
   int32_t *d_flat, *d_counts, *d_status, *d_ply, *d_err;
@@ -775,7 +874,8 @@ fpc_ctx *fpc_ctx_create(int device, int R, int max_n) {
   c->max_n = max_n;
   c->rec = fpc_record_bytes(R);
   const size_t n = (size_t)max_n;
-  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  c->stream = c->own_stream;
   ok = ok && cudaMalloc(&c->d_boards, n * c->rec) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_boards2, n * c->rec) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_start, c->rec) == cudaSuccess;
@@ -797,7 +897,7 @@ fpc_ctx *fpc_ctx_create(int device, int R, int max_n) {
 void fpc_ctx_destroy(fpc_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
   cudaFree(c->d_boards);
   cudaFree(c->d_boards2);
   cudaFree(c->d_start);
@@ -816,14 +916,30 @@ void fpc_ctx_destroy(fpc_ctx *c) {
 void *fpc_ctx_stream(fpc_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 
-static int ctx_check(fpc_ctx *c, int n, const char *who) {
+// The host-buffer calls run on the context's device and leave the caller's current device as they found it.
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  int enter(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev == dev) return FPC_OK;
+    int rc = cuda_check(cudaSetDevice(dev), "cudaSetDevice");
+    switched = rc == FPC_OK && prev >= 0;
+    return rc;
+  }
+  ~DevGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+static int ctx_check(fpc_ctx *c, int n, const char *who, DevGuard &guard) {
   if (!c) return fail(FPC_ERR_ARG, std::string(who) + ": null context");
   if (n < 0 || n > c->max_n) return fail(FPC_ERR_ARG, std::string(who) + ": n exceeds the context capacity");
-  return cuda_check(cudaSetDevice(c->device), "cudaSetDevice");
+  return guard.enter(c->device);
 }
 
 int fpc_ctx_sync(fpc_ctx *c) {
-  int rc = ctx_check(c, 0, "fpc_ctx_sync");
+  DevGuard guard_;
+  int rc = ctx_check(c, 0, "fpc_ctx_sync", guard_);
   if (rc != FPC_OK) return rc;
   rc = fpc_join(c->stream);
   if (rc != FPC_OK) return rc;
@@ -833,7 +949,8 @@ int fpc_ctx_sync(fpc_ctx *c) {
 int fpc_host_observe(fpc_ctx *c, const uint8_t *h_boards, int n, uint64_t *h_moves, int32_t *h_flat,
                      int32_t *h_counts, int32_t *h_status, float *h_planes, float *d_planes, int k_all,
                      float *h_mask, float *d_mask) {
-  int rc = ctx_check(c, n, "fpc_host_observe");
+  DevGuard guard_;
+  int rc = ctx_check(c, n, "fpc_host_observe", guard_);
   if (rc != FPC_OK) return rc;
   if (n == 0) return FPC_OK;
   if (!h_boards) return fail(FPC_ERR_ARG, "fpc_host_observe: null boards");
@@ -866,7 +983,8 @@ int fpc_host_observe(fpc_ctx *c, const uint8_t *h_boards, int n, uint64_t *h_mov
 
 static int host_make(fpc_ctx *c, const uint8_t *h_in, const uint64_t *h_moves, const int32_t *h_flat, int n,
                      uint8_t *h_out, int32_t *h_err) {
-  int rc = ctx_check(c, n, "fpc_host_make");
+  DevGuard guard_;
+  int rc = ctx_check(c, n, "fpc_host_make", guard_);
   if (rc != FPC_OK) return rc;
   if (n == 0) return FPC_OK;
   if (!h_in || !h_out || (!h_moves && !h_flat)) return fail(FPC_ERR_ARG, "fpc_host_make: null argument");
@@ -908,7 +1026,8 @@ static void *mapped_alias(const void *h) {
 int fpc_host_playout_step(fpc_ctx *c, uint8_t *h_boards, int n, uint64_t seed, uint64_t *h_game, int32_t *h_ply,
                           const uint8_t *h_start, int max_plies, uint64_t game_stride, int32_t *h_counts,
                           int32_t *h_status, float *d_planes, int k_all, float *d_mask, int flags) {
-  int rc = ctx_check(c, n, "fpc_host_playout_step");
+  DevGuard guard_;
+  int rc = ctx_check(c, n, "fpc_host_playout_step", guard_);
   if (rc != FPC_OK) return rc;
   if (n == 0) return FPC_OK;
   if (!h_boards || !h_game || !h_ply || !h_start) return fail(FPC_ERR_ARG, "fpc_host_playout_step: null argument");
@@ -954,6 +1073,288 @@ int fpc_host_playout_step(fpc_ctx *c, uint8_t *h_boards, int n, uint64_t seed, u
   if (rc != FPC_OK) return rc;
   CK(cudaStreamSynchronize(c->stream));
   return FPC_OK;
+}
+
+int fpc_ctx_set_stream(fpc_ctx *c, void *stream) {
+  if (!c) return fail(FPC_ERR_ARG, "fpc_ctx_set_stream: null context");
+  c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+  return FPC_OK;
+}
+
+int fpc_current_device(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(FPC_ERR_CUDA, "fpc_current_device: no usable CUDA device (there is no CPU fallback)");
+  }
+  return dev;
+}
+
+void *fpc_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cuda_check(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault), "cudaHostAlloc") != FPC_OK) return nullptr;
+  return p;
+}
+void fpc_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int fpc_host_expand(fpc_ctx *c, const uint8_t *h_parents, const uint64_t *h_moves, int n, uint8_t *h_children,
+                    int32_t *h_err, int32_t *h_counts, int32_t *h_status) {
+  DevGuard guard_;
+  int rc = ctx_check(c, n, "fpc_host_expand", guard_);
+  if (rc != FPC_OK) return rc;
+  if (n == 0) return FPC_OK;
+  if (!h_parents || !h_moves || !h_children) return fail(FPC_ERR_ARG, "fpc_host_expand: null argument");
+  const size_t N = (size_t)n;
+  CK(cudaMemcpyAsync(c->d_boards, h_parents, N * c->rec, cudaMemcpyHostToDevice, c->stream));
+  // the moves to make sit in the first n slots of the move buffer; the children's legal moves overwrite it afterwards
+  CK(cudaMemcpyAsync(c->d_moves, h_moves, N * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+  rc = fpc_make_moves(c->R, c->d_boards, c->d_moves, n, c->d_boards2, c->d_err, c->stream);
+  if (rc != FPC_OK) return rc;
+  rc = fpc_observe(c->R, c->d_boards2, n, c->d_moves, nullptr, c->d_counts, c->d_status, nullptr, nullptr, -1, nullptr, 0,
+                   c->stream);
+  if (rc != FPC_OK) return rc;
+  CK(cudaMemcpyAsync(h_children, c->d_boards2, N * c->rec, cudaMemcpyDeviceToHost, c->stream));
+  if (h_err) CK(cudaMemcpyAsync(h_err, c->d_err, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (h_counts) CK(cudaMemcpyAsync(h_counts, c->d_counts, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (h_status) CK(cudaMemcpyAsync(h_status, c->d_status, N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FPC_OK;
+}
+
+int fpc_host_fetch_moves(fpc_ctx *c, int n, int stride, uint64_t *h_moves) {
+  DevGuard guard_;
+  int rc = ctx_check(c, n, "fpc_host_fetch_moves", guard_);
+  if (rc != FPC_OK) return rc;
+  if (n == 0 || stride == 0) return FPC_OK;
+  if (!h_moves || stride < 0 || stride > FPC_MAX_MOVES) return fail(FPC_ERR_ARG, "fpc_host_fetch_moves: bad argument");
+  CK(cudaMemcpy2DAsync(h_moves, (size_t)stride * sizeof(uint64_t), c->d_moves, (size_t)FPC_MAX_MOVES * sizeof(uint64_t),
+                       (size_t)stride * sizeof(uint64_t), (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FPC_OK;
+}
+
+int fpc_host_encode(fpc_ctx *c, const uint8_t *h_boards, int n, int k_all, float *d_planes) {
+  DevGuard guard_;
+  int rc = ctx_check(c, n, "fpc_host_encode", guard_);
+  if (rc != FPC_OK) return rc;
+  if (n == 0) return FPC_OK;
+  if (!h_boards || !d_planes) return fail(FPC_ERR_ARG, "fpc_host_encode: null argument");
+  CK(cudaMemcpyAsync(c->d_boards, h_boards, (size_t)n * c->rec, cudaMemcpyHostToDevice, c->stream));
+  rc = fpc_encode(c->R, c->d_boards, n, nullptr, k_all, d_planes, 0, c->stream);
+  if (rc != FPC_OK) return rc;
+  CK(cudaStreamSynchronize(c->stream));  // the host buffer and d_boards are free again; the planes are complete
+  return FPC_OK;
+}
+
+int fpc_host_heuristic(fpc_ctx *c, const uint8_t *h_boards, int n, int32_t *h_value) {
+  DevGuard guard_;
+  int rc = ctx_check(c, n, "fpc_host_heuristic", guard_);
+  if (rc != FPC_OK) return rc;
+  if (n == 0) return FPC_OK;
+  if (!h_boards || !h_value) return fail(FPC_ERR_ARG, "fpc_host_heuristic: null argument");
+  CK(cudaMemcpyAsync(c->d_boards, h_boards, (size_t)n * c->rec, cudaMemcpyHostToDevice, c->stream));
+  rc = fpc_heuristic(c->R, c->d_boards, n, c->d_err, c->stream);
+  if (rc != FPC_OK) return rc;
+  CK(cudaMemcpyAsync(h_value, c->d_err, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FPC_OK;
+}
+
+int fpc_host_attack_maps(fpc_ctx *c, const uint8_t *h_boards, int n, uint8_t *h_out) {
+  DevGuard guard_;
+  int rc = ctx_check(c, n, "fpc_host_attack_maps", guard_);
+  if (rc != FPC_OK) return rc;
+  if (n == 0) return FPC_OK;
+  if (!h_boards || !h_out) return fail(FPC_ERR_ARG, "fpc_host_attack_maps: null argument");
+  const size_t nsq = (size_t)c->R * c->R;
+  uint8_t *d_out = reinterpret_cast<uint8_t *>(c->d_flat);  // [n][FPC_MAX_MOVES] int32 >= [n][R*R] bytes
+  CK(cudaMemcpyAsync(c->d_boards, h_boards, (size_t)n * c->rec, cudaMemcpyHostToDevice, c->stream));
+  rc = fpc_attack_maps(c->R, c->d_boards, n, d_out, c->stream);
+  if (rc != FPC_OK) return rc;
+  CK(cudaMemcpyAsync(h_out, d_out, (size_t)n * nsq, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FPC_OK;
+}
+
+// ---- environment-owned store + DLPack -------------------------------------------------------------------------
+
+struct fpc_env {
+  uint32_t magic;
+  int device, R, n, rec;
+  long refs;  // 1 for the owner until fpc_env_destroy, +1 per exported DLManagedTensor
+  cudaStream_t stream;
+  uint8_t *boards, *start;
+  uint64_t *moves, *game, *counters;
+  int32_t *flat, *counts, *status, *ply;
+  float *planes, *mask;
+};
+static constexpr uint32_t ENV_MAGIC = 0x46504345u;
+
+static void env_release(fpc_env *e) {
+  if (__atomic_sub_fetch(&e->refs, 1, __ATOMIC_ACQ_REL) != 0) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaSetDevice(e->device);
+  if (e->stream) {
+    cudaStreamSynchronize(e->stream);
+    cudaStreamDestroy(e->stream);
+  }
+  cudaFree(e->boards), cudaFree(e->start), cudaFree(e->moves), cudaFree(e->game), cudaFree(e->counters);
+  cudaFree(e->flat), cudaFree(e->counts), cudaFree(e->status), cudaFree(e->ply), cudaFree(e->planes), cudaFree(e->mask);
+  cudaSetDevice(dev);
+  e->magic = 0;
+  delete e;
+}
+
+static int env_check(fpc_env *e, const char *who, DevGuard &guard) {
+  if (!e || e->magic != ENV_MAGIC) return fail(FPC_ERR_ARG, std::string(who) + ": not an environment");
+  return guard.enter(e->device);
+}
+
+fpc_env *fpc_env_create(int device, int R, int n) {
+  if (!fpc_supported(R) || n <= 0) {
+    fail(FPC_ERR_ARG, "fpc_env_create: bad argument");
+    return nullptr;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    fail(FPC_ERR_CUDA, "fpc_env_create: no usable CUDA device (there is no CPU fallback)");
+    return nullptr;
+  }
+  if (cuda_check(cudaSetDevice(device), "cudaSetDevice") != FPC_OK) return nullptr;
+  fpc_env *e = new fpc_env();
+  memset(e, 0, sizeof *e);
+  e->magic = ENV_MAGIC, e->device = device, e->R = R, e->n = n, e->rec = fpc_record_bytes(R), e->refs = 1;
+  const size_t N = (size_t)n;
+  bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->boards, N * e->rec) == cudaSuccess && cudaMalloc(&e->start, e->rec) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->moves, N * FPC_MAX_MOVES * sizeof(uint64_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->flat, N * FPC_MAX_MOVES * sizeof(int32_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->game, N * sizeof(uint64_t)) == cudaSuccess && cudaMalloc(&e->counters, 8 * sizeof(uint64_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->counts, N * sizeof(int32_t)) == cudaSuccess && cudaMalloc(&e->status, N * sizeof(int32_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->ply, N * sizeof(int32_t)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->planes, N * fpc_state_space_size(R) * sizeof(float)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->mask, N * fpc_action_space_size(R) * sizeof(float)) == cudaSuccess;
+  if (ok) {
+    // game ids 0..n-1 (one id step per slot: game_stride = n re-seeds slot g with g + n, g + 2n, ...), ply 0
+    std::vector<uint64_t> ids(N);
+    for (size_t i = 0; i < N; ++i) ids[i] = i;
+    ok = cudaMemcpyAsync(e->game, ids.data(), N * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(e->ply, 0, N * sizeof(int32_t), e->stream) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(e->counters, 0, 8 * sizeof(uint64_t), e->stream) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(e->boards, 0, N * e->rec, e->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(e->stream) == cudaSuccess;
+  }
+  if (!ok) {
+    fail(FPC_ERR_CUDA, std::string("fpc_env_create: ") + cudaGetErrorString(cudaGetLastError()));
+    env_release(e);
+    return nullptr;
+  }
+  return e;
+}
+
+void fpc_env_destroy(fpc_env *e) {
+  if (e && e->magic == ENV_MAGIC) env_release(e);
+}
+void *fpc_env_stream(fpc_env *e) { return (e && e->magic == ENV_MAGIC) ? (void *)e->stream : nullptr; }
+int fpc_env_sync(fpc_env *e) {
+  DevGuard guard_;
+  int rc = env_check(e, "fpc_env_sync", guard_);
+  if (rc != FPC_OK) return rc;
+  return cuda_check(cudaStreamSynchronize(e->stream), "cudaStreamSynchronize");
+}
+
+int fpc_env_set_boards(fpc_env *e, const uint8_t *h_boards, int first, int count) {
+  DevGuard guard_;
+  int rc = env_check(e, "fpc_env_set_boards", guard_);
+  if (rc != FPC_OK) return rc;
+  if (!h_boards || first < 0 || count < 0 || first + count > e->n) return fail(FPC_ERR_ARG, "fpc_env_set_boards: bad range");
+  CK(cudaMemcpyAsync(e->boards + (size_t)first * e->rec, h_boards, (size_t)count * e->rec, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemsetAsync(e->ply + first, 0, (size_t)count * sizeof(int32_t), e->stream));
+  return cuda_check(cudaStreamSynchronize(e->stream), "cudaStreamSynchronize");  // the host buffer is free again
+}
+int fpc_env_get_boards(fpc_env *e, uint8_t *h_boards, int first, int count) {
+  DevGuard guard_;
+  int rc = env_check(e, "fpc_env_get_boards", guard_);
+  if (rc != FPC_OK) return rc;
+  if (!h_boards || first < 0 || count < 0 || first + count > e->n) return fail(FPC_ERR_ARG, "fpc_env_get_boards: bad range");
+  CK(cudaMemcpyAsync(h_boards, e->boards + (size_t)first * e->rec, (size_t)count * e->rec, cudaMemcpyDeviceToHost, e->stream));
+  return cuda_check(cudaStreamSynchronize(e->stream), "cudaStreamSynchronize");
+}
+
+int fpc_env_observe(fpc_env *e, int which, int k_all) {
+  DevGuard guard_;
+  int rc = env_check(e, "fpc_env_observe", guard_);
+  if (rc != FPC_OK) return rc;
+  return fpc_observe(e->R, e->boards, e->n, (which & FPC_ENV_MOVES) ? e->moves : nullptr, (which & FPC_ENV_FLAT) ? e->flat : nullptr,
+                     e->counts, e->status, (which & FPC_ENV_PLANES) ? e->planes : nullptr, nullptr, k_all,
+                     (which & FPC_ENV_MASK) ? e->mask : nullptr, 0, e->stream);
+}
+
+int fpc_env_playout_step(fpc_env *e, uint64_t seed, const uint8_t *h_start, int max_plies, uint64_t game_stride, int which,
+                         int k_all) {
+  DevGuard guard_;
+  int rc = env_check(e, "fpc_env_playout_step", guard_);
+  if (rc != FPC_OK) return rc;
+  if (!h_start) return fail(FPC_ERR_ARG, "fpc_env_playout_step: null start record");
+  CK(cudaMemcpyAsync(e->start, h_start, e->rec, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return fpc_playout_step(e->R, e->boards, e->n, seed, e->game, e->ply, e->start, max_plies, game_stride, nullptr, e->counts,
+                          e->status, (which & FPC_ENV_PLANES) ? e->planes : nullptr, nullptr, k_all,
+                          (which & FPC_ENV_MASK) ? e->mask : nullptr, e->counters, 0, e->stream);
+}
+
+struct EnvExport {
+  DLManagedTensor t;
+  int64_t shape[4];
+  fpc_env *env;
+};
+static void env_export_deleter(DLManagedTensor *self) {
+  if (!self) return;
+  EnvExport *x = static_cast<EnvExport *>(self->manager_ctx);
+  fpc_env *e = x->env;
+  delete x;
+  env_release(e);
+}
+
+DLManagedTensor *fpc_env_dlpack(fpc_env *e, int which) {
+  DevGuard guard_;
+  if (env_check(e, "fpc_env_dlpack", guard_) != FPC_OK) return nullptr;
+  EnvExport *x = new EnvExport();
+  memset(x, 0, sizeof *x);
+  DLTensor &d = x->t.dl_tensor;
+  const int R = e->R, A = fpc_num_action_channels(R);
+  d.shape = x->shape;
+  d.shape[0] = e->n;
+  d.ndim = 1;
+  switch (which) {
+    case FPC_ENV_BOARDS: d.data = e->boards, d.dtype = {kDLUInt, 8, 1}, d.ndim = 2, d.shape[1] = e->rec; break;
+    case FPC_ENV_COUNTS: d.data = e->counts, d.dtype = {kDLInt, 32, 1}; break;
+    case FPC_ENV_STATUS: d.data = e->status, d.dtype = {kDLInt, 32, 1}; break;
+    case FPC_ENV_PLY: d.data = e->ply, d.dtype = {kDLInt, 32, 1}; break;
+    case FPC_ENV_GAME: d.data = e->game, d.dtype = {kDLInt, 64, 1}; break;
+    case FPC_ENV_MOVES: d.data = e->moves, d.dtype = {kDLInt, 64, 1}, d.ndim = 2, d.shape[1] = FPC_MAX_MOVES; break;
+    case FPC_ENV_FLAT: d.data = e->flat, d.dtype = {kDLInt, 32, 1}, d.ndim = 2, d.shape[1] = FPC_MAX_MOVES; break;
+    case FPC_ENV_PLANES:
+      d.data = e->planes, d.dtype = {kDLFloat, 32, 1}, d.ndim = 4, d.shape[1] = FPC_NUM_STATE_CHANNELS, d.shape[2] = d.shape[3] = R;
+      break;
+    case FPC_ENV_MASK: d.data = e->mask, d.dtype = {kDLFloat, 32, 1}, d.ndim = 4, d.shape[1] = A, d.shape[2] = d.shape[3] = R; break;
+    default:
+      delete x;
+      fail(FPC_ERR_ARG, "fpc_env_dlpack: `which` must be exactly one FPC_ENV_* tensor");
+      return nullptr;
+  }
+  d.device = {kDLCUDA, e->device};
+  d.strides = nullptr;
+  d.byte_offset = 0;
+  x->env = e;
+  x->t.manager_ctx = x;
+  x->t.deleter = env_export_deleter;
+  __atomic_add_fetch(&e->refs, 1, __ATOMIC_ACQ_REL);
+  return &x->t;
 }
 
 }  // extern "C"

@@ -34,6 +34,7 @@
 #ifndef FPC_H_
 #define FPC_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -178,6 +179,14 @@ int fpc_playout_step(int R, uint8_t *d_boards, int n, uint64_t seed, uint64_t *d
                      int32_t *d_counts, int32_t *d_status, float *d_planes, const int32_t *d_k, int k_all,
                      float *d_mask, uint64_t *d_counters, int flags, void *stream);
 
+/* Viewer queries (src/cpp/board.cpp:120-232; the pygame UI only).  d_out [n][R*R] bytes, one per square in row-major
+ * order (every row / column, the cut corners included, as the reference's loops run):
+ *   bit c (0..3) = fpchess::Board::IsAttackedByPlayer(square, colour c) (src/cpp/board.cpp:142-209: rays bounded by the
+ *                  R x R index range only, so they run through the cut corners; a piece of another colour or a
+ *                  non-slider of the same colour blocks)
+ *   bit 4 + t    = chess::Board::IsAttackedByTeam(team t, square) (engine/board.cpp:606-786) */
+int fpc_attack_maps(int R, const uint8_t *d_boards, int n, uint8_t *d_out, void *stream);
+
 /* ---- batched PUCT: one warp owns one game's tree in HBM ---------------------------------------
  *
  * Replaces fpchess::Node (src/cpp/node.{h,cpp}) driven by MCTS.search / step / expand
@@ -268,6 +277,86 @@ int fpc_host_playout_step(fpc_ctx *ctx, uint8_t *h_boards, int n, uint64_t seed,
                           int32_t *h_counts, int32_t *h_status, float *d_planes, int k_all, float *d_mask,
                           int flags);
 int fpc_ctx_sync(fpc_ctx *ctx);
+
+/* Run the context's copies and kernels on `stream` (e.g. PyTorch's current stream, when outputs go into tensors that
+ * stream's allocator owns) instead of the context's own one; NULL switches back.  Host-buffer calls still return only
+ * when their results have landed. */
+int fpc_ctx_set_stream(fpc_ctx *ctx, void *stream);
+int fpc_current_device(void); /* cudaGetDevice, or a negative code */
+
+/* Page-locked host memory for the h_ buffers above (pageable memory works too, through the driver's staging). */
+void *fpc_host_alloc(size_t bytes); /* NULL on failure (fpc_last_error) */
+void fpc_host_free(void *p);
+
+/* Node::ExpandNodes (src/cpp/node.cpp:79-131) / Board::TakeAction (src/cpp/board.cpp:234-239) for a batch in ONE trip:
+ * child[i] = MakeMove(h_parents[i], h_moves[i]) (full 8-byte moves), and the observation of every child -- status word
+ * (GetGameResult + flags) and legal-move count -- so that the binding answers the children's GetGameResult /
+ * GetLegalMoves without another trip.  The children's legal moves stay in the context ([n][FPC_MAX_MOVES] on the
+ * device) until the next call through it; fpc_host_fetch_moves copies the first `stride` moves of each of the n rows
+ * to h_moves [n][stride] (stride = the largest count the caller needs).  h_flat (may be NULL) receives the flat
+ * action indices the same way when asked for in fpc_host_fetch_moves. */
+int fpc_host_expand(fpc_ctx *ctx, const uint8_t *h_parents, const uint64_t *h_moves, int n, uint8_t *h_children,
+                    int32_t *h_err, int32_t *h_counts, int32_t *h_status);
+int fpc_host_fetch_moves(fpc_ctx *ctx, int n, int stride, uint64_t *h_moves);
+/* Board::GetEncodedStates alone from host records into a device tensor (k_all as in fpc_encode). */
+int fpc_host_encode(fpc_ctx *ctx, const uint8_t *h_boards, int n, int k_all, float *d_planes);
+int fpc_host_heuristic(fpc_ctx *ctx, const uint8_t *h_boards, int n, int32_t *h_value);
+int fpc_host_attack_maps(fpc_ctx *ctx, const uint8_t *h_boards, int n, uint8_t *h_out);
+
+/* ---- environment-owned board store + DLPack -------------------------------------------------------
+ *
+ * For consumers that are not PyTorch: the library owns the device memory of n games (board records, per-game
+ * observation outputs, the dense planes / mask tensors) and hands any of them out as a DLPack DLManagedTensor
+ * (dlpack.h v0.8 layout, restated below so that this header stands alone), zero-copy.  The managed tensor keeps the
+ * environment alive: the store is freed when fpc_env_destroy has been called AND every exported tensor's deleter has
+ * run.  All work of an environment is ordered on its own stream (fpc_env_stream); fpc_env_sync waits for it. */
+typedef struct fpc_env fpc_env;
+fpc_env *fpc_env_create(int device, int R, int n); /* NULL on failure (fpc_last_error) */
+void fpc_env_destroy(fpc_env *env);
+void *fpc_env_stream(fpc_env *env);
+int fpc_env_sync(fpc_env *env);
+int fpc_env_set_boards(fpc_env *env, const uint8_t *h_boards, int first, int count); /* host records -> store */
+int fpc_env_get_boards(fpc_env *env, uint8_t *h_boards, int first, int count);
+/* fpc_observe over the store into the environment's own outputs (which = bit set of FPC_ENV_* below) */
+int fpc_env_observe(fpc_env *env, int which, int k_all);
+/* fpc_playout_step over the store (start record: host pointer), same outputs */
+int fpc_env_playout_step(fpc_env *env, uint64_t seed, const uint8_t *h_start, int max_plies, uint64_t game_stride,
+                         int which, int k_all);
+#define FPC_ENV_BOARDS 1   /* uint8  [n][record]            */
+#define FPC_ENV_COUNTS 2   /* int32  [n]                    */
+#define FPC_ENV_STATUS 4   /* int32  [n]                    */
+#define FPC_ENV_MOVES 8    /* int64  [n][FPC_MAX_MOVES]     */
+#define FPC_ENV_FLAT 16    /* int32  [n][FPC_MAX_MOVES]     */
+#define FPC_ENV_PLANES 32  /* float32 [n][24][R][R]         */
+#define FPC_ENV_MASK 64    /* float32 [n][8R+8][R][R]       */
+#define FPC_ENV_PLY 128    /* int32  [n]   (playout)        */
+#define FPC_ENV_GAME 256   /* int64  [n]   (playout)        */
+
+/* dlpack.h (v0.8) restated: identical layout, guarded so that a translation unit including the real header first
+ * keeps its definitions. */
+#ifndef DLPACK_DLPACK_H_
+typedef enum { kDLCPU = 1, kDLCUDA = 2, kDLCUDAHost = 3 } DLDeviceType;
+typedef struct { DLDeviceType device_type; int32_t device_id; } DLDevice;
+typedef enum { kDLInt = 0U, kDLUInt = 1U, kDLFloat = 2U } DLDataTypeCode;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;
+typedef struct {
+  void *data;
+  DLDevice device;
+  int32_t ndim;
+  DLDataType dtype;
+  int64_t *shape;
+  int64_t *strides; /* NULL = compact row-major */
+  uint64_t byte_offset;
+} DLTensor;
+typedef struct DLManagedTensor {
+  DLTensor dl_tensor;
+  void *manager_ctx;
+  void (*deleter)(struct DLManagedTensor *self);
+} DLManagedTensor;
+#endif
+/* One of the FPC_ENV_* tensors as a DLManagedTensor (the consumer calls ->deleter when done; wrap it in a PyCapsule
+ * named "dltensor" for torch.utils.dlpack.from_dlpack / cupy.from_dlpack).  NULL on failure. */
+DLManagedTensor *fpc_env_dlpack(fpc_env *env, int which);
 
 #ifdef __cplusplus
 }

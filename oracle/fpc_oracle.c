@@ -512,6 +512,73 @@ int fpo_is_attacked_by_team(int R, int IA, const uint8_t *rec, int team, int sq)
   Geo g = geo(R, IA);
   return attacked_by_team(&g, rec, team, sq);
 }
+/* fpchess::Board::IsAttackedByPlayer (src/cpp/board.cpp:142-209), the viewer's query.  Its "isLegalPosition" is
+ * BoardLocation::Present(), i.e. inside the R x R index range: rays run through the cut corners. */
+static int attacked_by_player(const Geo *g, const uint8_t *b, int sq, int color) {
+  static const int D8[8][2] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}, {1, 1}, {1, -1}, {-1, 1}, {-1, -1}};
+  static const int KN[8][2] = {{1, 2}, {2, 1}, {-1, -2}, {-2, -1}, {1, -2}, {2, -1}, {-1, 2}, {-2, 1}};
+  int R = g->R, lr = sq / R, lc = sq % R;
+  /* pawns (:153-162): a pawn of that colour on a neighbour that PawnAttacks (engine/board.cpp:583-604) the square */
+  for (int d = 0; d < 8; ++d) {
+    int r = lr + D8[d][0], c = lc + D8[d][1];
+    if (r < 0 || r >= R || c < 0 || c >= R) continue;
+    uint8_t p = b[r * R + c];
+    if (color_of(p) == color && type_of(p) == PAWN) {
+      int rd = lr - r, cd = lc - c, a = 0;
+      switch (color) {
+        case RED: a = rd == -1 && abs(cd) == 1; break;
+        case BLUE: a = cd == 1 && abs(rd) == 1; break;
+        case YELLOW: a = rd == 1 && abs(cd) == 1; break;
+        case GREEN: a = cd == -1 && abs(rd) == 1; break;
+      }
+      if (a) return 1;
+    }
+  }
+  /* knights (:165-171) */
+  for (int d = 0; d < 8; ++d) {
+    int r = lr + KN[d][0], c = lc + KN[d][1];
+    if (r < 0 || r >= R || c < 0 || c >= R) continue;
+    uint8_t p = b[r * R + c];
+    if (color_of(p) == color && type_of(p) == KNIGHT) return 1;
+  }
+  /* bishops, rooks, queens (:174-199): the first piece on a ray decides */
+  for (int d = 0; d < 8; ++d) {
+    int dr = D8[d][0], dc = D8[d][1], r = lr + dr, c = lc + dc;
+    for (; r >= 0 && r < R && c >= 0 && c < R; r += dr, c += dc) {
+      uint8_t p = b[r * R + c];
+      if (!present(p)) continue;
+      if (color_of(p) != color) break;
+      int t = type_of(p);
+      if (t != BISHOP && t != ROOK && t != QUEEN) break;
+      if (t == BISHOP && (dr == 0 || dc == 0)) break;
+      if (t == ROOK && dr != 0 && dc != 0) break;
+      return 1;
+    }
+  }
+  /* kings (:202-207) */
+  for (int d = 0; d < 8; ++d) {
+    int r = lr + D8[d][0], c = lc + D8[d][1];
+    if (r < 0 || r >= R || c < 0 || c >= R) continue;
+    uint8_t p = b[r * R + c];
+    if (color_of(p) == color && type_of(p) == KING) return 1;
+  }
+  return 0;
+}
+int fpo_is_attacked_by_player(int R, int IA, const uint8_t *rec, int sq, int color) {
+  Geo g = geo(R, IA);
+  return attacked_by_player(&g, rec, sq, color);
+}
+/* the byte map of fpc_attack_maps (include/fpc.h): bit c = IsAttackedByPlayer(colour c), bit 4+t = IsAttackedByTeam(t),
+ * for every square of the R x R box (GetAttackedSquaresPlayers / Teams, src/cpp/board.cpp:120-140, 211-232) */
+void fpo_attack_map(int R, int IA, const uint8_t *rec, uint8_t *out) {
+  Geo g = geo(R, IA);
+  for (int sq = 0; sq < g.nsq; ++sq) {
+    int bits = 0;
+    for (int c = 0; c < 4; ++c) bits |= attacked_by_player(&g, rec, sq, c) << c;
+    for (int t = 0; t < 2; ++t) bits |= attacked_by_team(&g, rec, t, sq) << (4 + t);
+    out[sq] = (uint8_t)bits;
+  }
+}
 int fpo_king_in_check(int R, int IA, const uint8_t *rec, int color) {
   Geo g = geo(R, IA);
   int k = rec[g.off_king + color];

@@ -35,6 +35,8 @@ def lib():
         L.fpo_legal_moves.argtypes = [C.c_int, C.c_int, _u8p, _u64p, C.c_int]
         L.fpo_is_attacked_by_team.argtypes = [C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
         L.fpo_king_in_check.argtypes = [C.c_int, C.c_int, _u8p, C.c_int]
+        L.fpo_is_attacked_by_player.argtypes = [C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
+        L.fpo_attack_map.argtypes = [C.c_int, C.c_int, _u8p, _u8p]
         L.fpo_make_move.argtypes = [C.c_int, C.c_int, _u8p, C.c_uint64, _u8p]
         L.fpo_make_index.argtypes = [C.c_int, C.c_int, _u8p, C.c_int, _u8p]
         L.fpo_move_from_flat.argtypes = [C.c_int, C.c_int]
@@ -84,6 +86,16 @@ class Oracle:
 
     def is_attacked_by_team(self, rec, team, sq) -> bool:
         return bool(self.L.fpo_is_attacked_by_team(self.R, self.IA, np.ascontiguousarray(rec), team, sq))
+
+    def is_attacked_by_player(self, rec, sq, color) -> bool:
+        """fpchess::Board::IsAttackedByPlayer (src/cpp/board.cpp:142-209)."""
+        return bool(self.L.fpo_is_attacked_by_player(self.R, self.IA, np.ascontiguousarray(rec), sq, color))
+
+    def attack_map(self, rec) -> np.ndarray:
+        """[R*R] u8: bit c = IsAttackedByPlayer(colour c), bit 4+t = IsAttackedByTeam(team t)."""
+        out = np.zeros(self.R * self.R, dtype=np.uint8)
+        self.L.fpo_attack_map(self.R, self.IA, np.ascontiguousarray(rec), out)
+        return out
 
     def king_in_check(self, rec, color) -> bool:
         return bool(self.L.fpo_king_in_check(self.R, self.IA, np.ascontiguousarray(rec), color))

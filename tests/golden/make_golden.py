@@ -17,7 +17,11 @@ REFERENCE ITSELF in the build container (it cannot travel to the GPU box):
                       children (flat action indices, visit counts), the root's visit count and the
                       number of nodes in the tree (the binding exposes neither priors nor value sums).
 
+  viewer_R<R>.npz     the viewer's queries of the reference binding (attacked squares per colour / team,
+                      GetSimpleState) on the same positions.
+
 usage:  python tests/golden/make_golden.py            # everything (needs /root/reference)
+        python tests/golden/make_golden.py --viewer-only  # only viewer_R*.npz
         python tests/golden/make_golden.py --binding 14   # (internal) one binding geometry
 """
 from __future__ import annotations
@@ -237,9 +241,67 @@ def make_binding(R: int):
     print(path, os.path.getsize(path))
 
 
+def make_viewer(R: int):
+    """viewer_R<R>.npz: the pygame viewer's queries of the reference binding (src/cpp/board.cpp:50-57,120-232) on the
+    positions of binding_R<R>.npz: per square the colours / teams that attack it (GetAttackedSquaresPlayers /
+    GetAttackedSquaresTeams / IsAttackedByPlayer) and GetSimpleState's fields."""
+    import alphazero_cpp as az
+
+    nsq = R * R
+    z = np.load(os.path.join(HERE, f"binding_R{R}.npz"))
+    recs = z["recs"][:64]
+
+    def board_from_record(rec):
+        pieces = {}
+        for sq in range(nsq):
+            b = int(rec[sq])
+            if b & 0x80:
+                pieces[az.BoardLocation(sq // R, sq % R)] = az.Piece(az.PlayerColor((b >> 5) & 3), az.PieceType((b >> 2) & 7))
+        return az.Board(az.Player(az.PlayerColor(int(rec[nsq]))), pieces)
+
+    maps, simple_pieces, simple_turn = [], [], []
+    for rec in recs:
+        b = board_from_record(rec)
+        m = np.zeros(nsq, dtype=np.uint8)
+        players = b.GetAttackedSquaresPlayers()
+        for color, locs in players.items():
+            for loc in locs:
+                m[loc.GetRow() * R + loc.GetCol()] |= 1 << int(color)
+        for team, locs in b.GetAttackedSquaresTeams().items():
+            for loc in locs:
+                m[loc.GetRow() * R + loc.GetCol()] |= 16 << int(team)
+        for sq in range(0, nsq, 7):  # the single-square query agrees with the map
+            for c in range(4):
+                assert b.IsAttackedByPlayer(az.BoardLocation(sq // R, sq % R), az.PlayerColor(c)) == bool((m[sq] >> c) & 1)
+        st = b.GetSimpleState()
+        assert {int(k): sorted(l.GetRow() * R + l.GetCol() for l in v) for k, v in st.attackedSquares.items()} == \
+               {int(k): sorted(l.GetRow() * R + l.GetCol() for l in v) for k, v in players.items()}
+        simple_turn.append(int(st.turn.GetColor()))
+        simple_pieces.append(sorted((int(pp.GetPiece().GetColor()), int(pp.GetPiece().GetPieceType()),
+                                     pp.GetLocation().GetRow() * R + pp.GetLocation().GetCol())
+                                    for pl in st.pieces for pp in pl))
+        assert len(st.castlingRights) == 4
+        maps.append(m)
+    flat = np.array([x for sp in simple_pieces for x in sp], dtype=np.int32).reshape(-1, 3)
+    off = np.cumsum([0] + [len(sp) for sp in simple_pieces]).astype(np.int64)
+    path = os.path.join(HERE, f"viewer_R{R}.npz")
+    np.savez_compressed(path, recs=recs, attack_map=np.stack(maps), simple_turn=np.array(simple_turn, dtype=np.int32),
+                        simple_pieces=flat, simple_pieces_off=off)
+    print(path, os.path.getsize(path))
+
+
 def main():
     if "--binding" in sys.argv:
         make_binding(int(sys.argv[sys.argv.index("--binding") + 1]))
+        return
+    if "--viewer" in sys.argv:
+        make_viewer(int(sys.argv[sys.argv.index("--viewer") + 1]))
+        return
+    if "--viewer-only" in sys.argv:  # add the viewer fixtures without regenerating the others
+        for R in (14, 8):
+            bdir = os.path.join(ROOT, "oracle", "_ref", f"binding_R{R}")
+            env = dict(os.environ, PYTHONPATH=os.pathsep.join([bdir, REF_PY, "/root/reference", ROOT]))
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), "--viewer", str(R)], env=env)
         return
     if not os.path.isdir(REF_PY):
         raise SystemExit("the reference tree is needed to regenerate the golden fixtures")
@@ -251,6 +313,7 @@ def main():
             subprocess.check_call(["bash", os.path.join(ROOT, "oracle", "build_ref_binding.sh"), str(R), str(IA)])
         env = dict(os.environ, PYTHONPATH=os.pathsep.join([bdir, REF_PY, "/root/reference", ROOT]))
         subprocess.check_call([sys.executable, os.path.abspath(__file__), "--binding", str(R)], env=env)
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "--viewer", str(R)], env=env)
 
 
 if __name__ == "__main__":

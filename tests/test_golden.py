@@ -147,3 +147,18 @@ def test_mcts_fixtures(R, case):
         assert t.visits[0] == int(z[f"{case}_root_visits"][gi])
         assert len(t.parent) == int(z[f"{case}_n_nodes"][gi])
     assert net.calls == int(z[f"{case}_nn_calls"]) and net.positions == int(z[f"{case}_nn_positions"])
+
+
+@pytest.mark.parametrize("R", [14, 8])
+def test_viewer_fixtures(R):
+    """Attacked squares per colour / team (the pygame viewer's queries, src/cpp/board.cpp:120-232) as the reference's
+    own binding reported them."""
+    o = oracle_for(R)
+    z = load(f"viewer_R{R}.npz")
+    assert z["attack_map"].any()
+    for rec, want in zip(z["recs"], z["attack_map"]):
+        got = o.attack_map(rec)
+        assert np.array_equal(got, want)
+        for sq in range(0, R * R, 11):
+            for c in range(4):
+                assert o.is_attacked_by_player(rec, sq, c) == bool((want[sq] >> c) & 1)
