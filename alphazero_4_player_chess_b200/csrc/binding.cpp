@@ -199,7 +199,7 @@ struct Pinned {  // a growing page-locked buffer (fpc_host_alloc)
     const size_t bytes = count * sizeof(T);
     if (bytes > cap) {
       if (p) fpc_host_free(p);
-      cap = std::max(bytes * 2, (size_t)4096);
+      cap = std::max(bytes * 2, (size_t)1 << 20);  // page-locking is slow: few, large steps
       p = fpc_host_alloc(cap);
       if (!p) {
         cap = 0;

@@ -44,19 +44,89 @@ class PolicyValueNet(nn.Module):
 
 
 class InferenceNet:
-    """Eval-mode wrapper used inside the search loop: bf16 weights + channels_last,
-    f32 logits / values out, same call contract as the reference's `self.neural_net(encoded)`."""
+    """Eval-mode inference view used inside the search loop, same call contract as the reference's
+    `self.neural_net(encoded)`: f32 planes in, f32 logits / values out.  The network stays PyTorch / cuDNN / cuBLAS --
+    this only removes the passes over the activations that inference does not need:
 
-    def __init__(self, net: PolicyValueNet, bf16: bool = True):
+      * BatchNorm (eval: running statistics) is folded into the preceding convolution's weights and bias, once;
+      * convolution + bias + ReLU, and convolution + bias + residual + ReLU, each run as ONE cuDNN call
+        (`torch.cudnn_convolution_relu` / `cudnn_convolution_add_relu`) in channels_last: 23 kernels for the 10-block
+        tower instead of ~85;
+      * the two heads' Linear weights have their input columns permuted from (c, h, w) to (h, w, c) order, so Flatten of
+        the channels_last activation is a view instead of a transposing copy;
+      * bf16=True: bf16 weights and activations (the 553 M-parameter policy Linear converted once, not per call);
+        bf16=False: fp32 throughout = the reference's precision (`src/py/net.py` under PyTorch defaults).
+
+    The wrapped module is left untouched (fp32, trainable); call refresh() after its weights change."""
+
+    def __init__(self, net: PolicyValueNet, bf16: bool = True, fused: bool = True):
         self.dtype = torch.bfloat16 if bf16 else torch.float32
-        # weights converted once (autocast would re-cast the 553 M-parameter policy Linear every call)
-        self.net = net.eval().to(dtype=self.dtype, memory_format=torch.channels_last)
+        self.module = net
         self.device = net.device
+        self.fused = bool(fused) and self.device.type == "cuda" and self._fused_ops_work()
+        self.refresh()
+
+    # ---- weights ----------------------------------------------------------------------------------------
+    @staticmethod
+    def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+        """conv -> BN(eval) as one convolution: w * g / sqrt(var + eps), (b - mean) * g / sqrt(var + eps) + beta (fp32)."""
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        w = conv.weight.detach().float() * scale.view(-1, 1, 1, 1)
+        b = (conv.bias.detach().float() - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+        return w, b
+
+    def _conv(self, conv: nn.Conv2d, bn: nn.BatchNorm2d):
+        w, b = self._fold(conv, bn)
+        return (w.to(self.dtype).contiguous(memory_format=torch.channels_last), b.to(self.dtype).contiguous())
+
+    def _head_linear(self, lin: nn.Linear, channels: int):
+        out_f, in_f = lin.weight.shape
+        w = lin.weight.detach().view(out_f, channels, in_f // channels).permute(0, 2, 1).reshape(out_f, in_f)
+        return w.to(self.dtype).contiguous(), lin.bias.detach().to(self.dtype).contiguous()
+
+    @torch.no_grad()
+    def refresh(self) -> None:
+        m = self.module
+        self.stem = self._conv(m.stem[0], m.stem[1])
+        self.tower = [(self._conv(r.a[0], r.a[1]), self._conv(r.a[3], r.a[4])) for r in m.tower]
+        self.p_conv = self._conv(m.policy[0][0], m.policy[0][1])
+        self.v_conv = self._conv(m.value[0][0], m.value[0][1])
+        self.p_lin = self._head_linear(m.policy[2], m.policy[0][0].out_channels)
+        self.v_lin = self._head_linear(m.value[2], m.value[0][0].out_channels)
+
+    def _fused_ops_work(self) -> bool:
+        try:
+            x = torch.zeros((1, 8, 4, 4), dtype=self.dtype, device=self.device).contiguous(memory_format=torch.channels_last)
+            w = torch.zeros((8, 8, 3, 3), dtype=self.dtype, device=self.device).contiguous(memory_format=torch.channels_last)
+            b = torch.zeros(8, dtype=self.dtype, device=self.device)
+            y = torch.cudnn_convolution_relu(x, w, b, (1, 1), (1, 1), (1, 1), 1)
+            torch.cudnn_convolution_add_relu(x, w, y, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
+            return True
+        except Exception:
+            return False
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def _conv_relu(self, x, wb):
+        if self.fused:
+            return torch.cudnn_convolution_relu(x, wb[0], wb[1], (1, 1), (1, 1), (1, 1), 1)
+        return torch.relu_(torch.nn.functional.conv2d(x, wb[0], wb[1], padding=1))
+
+    def _conv_add_relu(self, x, wb, residual):
+        if self.fused:
+            return torch.cudnn_convolution_add_relu(x, wb[0], residual, 1.0, wb[1], (1, 1), (1, 1), (1, 1), 1)
+        return torch.relu_(torch.nn.functional.conv2d(x, wb[0], wb[1], padding=1).add_(residual))
 
     @torch.no_grad()
     def __call__(self, planes: torch.Tensor):
+        n = planes.shape[0]
         x = planes.to(self.dtype).contiguous(memory_format=torch.channels_last)
-        logits, value = self.net(x)
+        x = self._conv_relu(x, self.stem)
+        for a, b in self.tower:
+            x = self._conv_add_relu(self._conv_relu(x, a), b, x)
+        p = self._conv_relu(x, self.p_conv).permute(0, 2, 3, 1).reshape(n, -1)  # (h, w, c) order: a view
+        v = self._conv_relu(x, self.v_conv).permute(0, 2, 3, 1).reshape(n, -1)
+        logits = torch.nn.functional.linear(p, self.p_lin[0], self.p_lin[1])
+        value = torch.tanh(torch.nn.functional.linear(v, self.v_lin[0], self.v_lin[1]))
         return logits.float(), value.float()
 
 

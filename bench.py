@@ -621,7 +621,7 @@ def dropin_leg() -> dict:
             if r.returncode != 0 or not line:
                 out[which] = {"unavailable": (r.stderr or r.stdout)[-200:]}
                 continue
-            out[which] = {"value": float(line[-1].split("=")[1].split()[0]), "unit": "sims/s", "line": line[-1]}
+            out[which] = {"value": float(line[-1].split("=")[1].split()[0]), "unit": "sims/s", "line": line[-1]}  # the median
         except Exception as e:  # pragma: no cover
             out[which] = {"unavailable": repr(e)}
     if "value" in out.get("ours", {}) and "value" in out.get("ref", {}):

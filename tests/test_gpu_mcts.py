@@ -235,3 +235,43 @@ def test_configs3_search_replayed_on_the_oracle():
         assert value_sum[i, :nn].tolist() == t.value_sum
     print(f"configs[3]: {n} games x {sims} sims, {int(m.n_nodes.sum())} nodes; {len(trees)} games replayed on the oracle, "
           f"{sum(len(t.parent) for t in trees)} nodes identical")
+
+
+def test_inference_net_equals_the_module_it_wraps():
+    """InferenceNet (BatchNorm folded, fused cuDNN conv+bias+ReLU(+residual), permuted head weights) against the plain
+    eval-mode module.  fp32 = the reference's precision = PyTorch defaults, under which cuDNN convolutions use TF32 on both
+    sides (torch.backends.cudnn.allow_tf32 is True by default, matmuls stay fp32): 3e-3 of the logit magnitude; with TF32
+    off on both sides 2e-5; bf16 within 6e-2."""
+    from alphazero_4_player_chess_b200.net import InferenceNet, PolicyValueNet
+    torch.manual_seed(1)
+    R = 14
+    m = PolicyValueNet(R, 3, 32, device="cuda")
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_()
+            mod.running_var.uniform_(0.5, 2.0)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_()
+    m.eval()
+    x = (torch.rand(64, 24, R, R, device="cuda") < 0.05).float()
+    with torch.no_grad():
+        l0, v0 = m(x)
+    def check(tol, bf16, want_l, want_v):
+        for fused in (True, False):
+            inf = InferenceNet(m, bf16=bf16, fused=fused)
+            l1, v1 = inf(x)
+            assert l1.dtype == torch.float32 and l1.shape == want_l.shape and v1.shape == want_v.shape
+            assert float((l1 - want_l).abs().max()) < tol * max(1.0, float(want_l.abs().max())), (bf16, fused)
+            assert float((v1 - want_v).abs().max()) < tol, (bf16, fused)
+
+    check(3e-3, False, l0, v0)
+    check(6e-2, True, l0, v0)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            l2, v2 = m(x)
+        check(2e-5, False, l2, v2)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    assert next(m.parameters()).dtype == torch.float32  # the wrapped module is left as it was

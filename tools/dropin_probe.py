@@ -27,10 +27,24 @@ net = FakeNet(R, device="cuda")
 games = [board_from_record(az, rec, R) for _ in range(8)]
 drive_search(az, games, net, 3, 4)  # warm-up
 torch.cuda.synchronize()
-games = [board_from_record(az, rec, R) for _ in range(games_n)]
-t0 = time.perf_counter()
-roots = drive_search(az, games, net, 3, sims)
-torch.cuda.synchronize()
-dt = time.perf_counter() - t0
-visits = sum(r.GetVisitCount() for r in roots)
-print(f"{which}: {games_n} games x {sims} sims in {dt:.2f} s = {games_n * sims / dt:.0f} sims/s (root visits {visits})", flush=True)
+reps = 1 if "--profile" in sys.argv else 3
+rates = []
+for rep in range(reps):
+    games = [board_from_record(az, rec, R) for _ in range(games_n)]
+    if "--profile" in sys.argv:
+        import cProfile, pstats
+        pr = cProfile.Profile()
+        pr.enable()
+    t0 = time.perf_counter()
+    roots = drive_search(az, games, net, 3, sims)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if "--profile" in sys.argv:
+        pr.disable()
+        pstats.Stats(pr).sort_stats("tottime").print_stats(18)
+    rates.append(games_n * sims / dt)
+    visits = sum(r.GetVisitCount() for r in roots)
+    del roots, games
+rates.sort()
+print(f"{which}: {games_n} games x {sims} sims, median of {reps} = {rates[len(rates) // 2]:.0f} sims/s (all: "
+      f"{', '.join(f'{r:.0f}' for r in rates)}; root visits {visits})", flush=True)
