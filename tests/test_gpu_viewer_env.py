@@ -91,6 +91,7 @@ def test_dropin_children_carry_their_observation(az):
     recs = mixed_positions("STANDARD", 96)[::4]
     for rec in recs:
         b = board_from_record(az, rec, R)
+        rec = np.frombuffer(b.record(), dtype=np.uint8).copy()  # the Python constructor path carries no castling rights
         legal = b.GetLegalMoves()
         assert [m.image() for m in legal] == [int(m) for m in sorted(o.legal_moves(rec), key=lambda m: (o.move_flat_index(int(m)), (int(m) >> 24) & 0xff))]
         for m in legal[:: max(1, len(legal) // 4)]:
