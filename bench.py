@@ -311,7 +311,7 @@ def run_ours(args) -> None:
         env.playout_step(seed=SEED, max_plies=MAX_PLIES, game_stride=stride, planes=True, mask=True, k=-1,
                          async_dense=True)
 
-    fast_forward(env, start, stride, torch)  # untimed: the resident games now span whole games
+    fast_forward(env, start, stride, torch, plies=args.ff)  # untimed: the resident games now span whole games
     for _ in range(max(args.warmup, 3)):
         step()
     env.join()
@@ -369,7 +369,7 @@ def run_ours(args) -> None:
     if world == 1:
         start_off = start_record("STANDARD", castling=False)
         env.reset_playout(start_off, first_game=shard.first_game)
-        fast_forward(env, start_off, stride, torch)
+        fast_forward(env, start_off, stride, torch, plies=args.ff)
         for _ in range(3):
             step()
         env.join()
@@ -564,7 +564,7 @@ def mcts_leg(rank: int, world: int, local: int) -> dict:
         torch.cuda.synchronize()
         total_ms = e0.elapsed_time(e1)
         m.check_errors()
-        nodes = int(m.n_nodes.sum().item())
+        nodes, max_nodes = int(m.n_nodes.sum().item()), int(m.n_nodes.max().item())
         # the network alone on the same leaf batch, and the tree kernels alone (fixed network outputs)
         x = m.planes
         for _ in range(2):
@@ -596,7 +596,7 @@ def mcts_leg(rank: int, world: int, local: int) -> dict:
                      "ms_per_sim_batch": total_ms / sims, "network_alone_ms_per_batch": net_ms,
                      "network_share": min(1.0, net_ms / (total_ms / sims)),
                      "tree_kernels_only": {"value": n_games / (tree_ms * 1e-3), "unit": "sims/s", "ms_per_sim_batch": tree_ms},
-                     "nodes": nodes, "max_nodes_per_game": int(m.n_nodes.max().item()), "node_cap": m.node_cap,
+                     "nodes": nodes, "max_nodes_per_game": max_nodes, "node_cap": m.node_cap,
                      "tree_bytes": tree_bytes, "precision": "fp32 (PyTorch defaults: the reference's)" if not bf16 else "bf16 weights + activations"}
         if sims != sims_full:
             out[name]["note"] = f"{sims}-simulation sample of the {sims_full}-simulation search"
@@ -667,6 +667,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mcts", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
+    ap.add_argument("--ff", type=int, default=FAST_FORWARD,
+                    help="untimed rules-only plies that spread the resident games over whole games (profiling runs shorten it)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
