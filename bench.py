@@ -173,10 +173,38 @@ def reference_full_path(steps: int, warmup: int, n_games: int) -> dict | None:
         return None
     threads = host_threads()
     # the Python path of the reference builds boards without castling rights (fen_parser.py:137-140,170)
-    r = ref_binding_env.run(R, start_record("STANDARD", castling=False), n_games, steps, warmup, threads,
-                            max_plies=MAX_PLIES, seed=SEED)
+    start = start_record("STANDARD", castling=False)
+    initial, plies = whole_game_mix(start, n_games, threads)
+    r = ref_binding_env.run(R, start, n_games, steps, warmup, threads, max_plies=MAX_PLIES, seed=SEED,
+                            initial=initial, initial_plies=plies)
     return {"value": r["positions_per_s"], "unit": UNIT, "cores": r["procs"], "seconds": r["seconds"],
-            "positions": r["positions"]}
+            "positions": r["positions"], "mix": "whole games" if initial is not None else "from the start position"}
+
+
+def whole_game_mix(start, n_games: int, threads: int):
+    """The same position mix as our arm's fast-forward, for the reference arm: slot i starts about 2048 * i / n plies
+    into a random playout (games that end earlier have re-seeded themselves), played by the unmodified reference engine
+    (oracle/_ref, all host threads, ~2 s, untimed).  None where the engine library is not built."""
+    import numpy as np
+
+    from oracle import ref_engine
+    if not ref_engine.available(R):
+        return None, None
+    env = ref_engine.RefEnv(ref_engine.RefEngine(R), start, n_games, SEED, n_threads=threads, max_plies=MAX_PLIES)
+    target = (np.arange(n_games, dtype=np.int64) * FAST_FORWARD) // n_games
+    recs = np.zeros((n_games, len(start)), dtype=np.uint8)
+    plies = np.zeros(n_games, dtype=np.int64)
+    nxt = 0
+    for step in range(FAST_FORWARD):
+        while nxt < n_games and target[nxt] == step:
+            recs[nxt], _, plies[nxt] = env.get(nxt)
+            nxt += 1
+        env.step()
+    while nxt < n_games:
+        recs[nxt], _, plies[nxt] = env.get(nxt)
+        nxt += 1
+    env.close()
+    return recs, plies
 
 
 def run_reference(args) -> None:
@@ -203,7 +231,7 @@ def run_reference(args) -> None:
     value = full["value"]
     sample = (f"{args.steps} steps x {sample_games} of the {N_GAMES} resident games, castling rights OFF (the reference's "
               "Python API cannot pass rights to Board(): its Player type is unhashable, fen_parser.py drops them; our "
-              f"arm reports this start record as `castling_off`), games from the start position; {kind_note}")
+              f"arm reports this start record as `castling_off`), slots spread over whole games like our arm's ({full.get('mix')}); {kind_note}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sample_games / value * 1e3,
@@ -226,9 +254,9 @@ def cpu_baseline_leg() -> dict:
     full = reference_full_path(steps=300, warmup=3, n_games=1024)
     if full is not None:
         return {"value": full["value"], "unit": UNIT, "cores": full["cores"], "kind": "reference",
-                "sample": f"300 plies x 1024 games ({full['positions']} positions, {full['seconds']:.1f} s) through the "
-                          "unmodified reference binding: engine + GetEncodedStates + legal mask on CPU tensors, one "
-                          "process per core", "engine_only": eng}
+                "sample": f"300 plies x 1024 games ({full['positions']} positions, {full['seconds']:.1f} s; slots spread over "
+                          f"{full.get('mix')}, castling rights off) through the unmodified reference binding: engine + "
+                          "GetEncodedStates + legal mask on CPU tensors, one process per core", "engine_only": eng}
     if eng is not None:
         return {"value": eng["value"], "unit": UNIT, "cores": threads, "kind": "reference", "sample": eng["sample"]}
     from oracle.port import Oracle

@@ -35,15 +35,15 @@ def available(R: int) -> bool:
     return os.path.exists(os.path.join(binding_dir(R), "alphazero_cpp.so"))
 
 
-def _worker(R, start_rec, n_slots, steps, warmup, max_plies, seed, barrier, out_q):
+def _worker(R, start_rec, n_slots, steps, warmup, max_plies, seed, barrier, out_q, initial=None, initial_plies=None):
     try:
-        _work(R, start_rec, n_slots, steps, warmup, max_plies, seed, barrier, out_q)
+        _work(R, start_rec, n_slots, steps, warmup, max_plies, seed, barrier, out_q, initial, initial_plies)
     except BaseException as e:  # never leave the other processes waiting at a barrier
         barrier.abort()
         out_q.put(("error", repr(e)))
 
 
-def _work(R, start_rec, n_slots, steps, warmup, max_plies, seed, barrier, out_q):
+def _work(R, start_rec, n_slots, steps, warmup, max_plies, seed, barrier, out_q, initial=None, initial_plies=None):
     import random
 
     import torch
@@ -64,9 +64,21 @@ def _work(R, start_rec, n_slots, steps, warmup, max_plies, seed, barrier, out_q)
     def fresh():
         return az.Board(turn, pieces)
 
+    def from_record(rec):
+        pcs = {}
+        for sq in range(nsq):
+            b = int(rec[sq])
+            if b & 0x80:
+                pcs[az.BoardLocation(sq // R, sq % R)] = az.Piece(az.PlayerColor((b >> 5) & 3), az.PieceType((b >> 2) & 7))
+        return az.Board(az.Player(az.PlayerColor(int(rec[nsq]))), pcs)
+
     rng = random.Random(seed)
-    states = [fresh() for _ in range(n_slots)]
-    plies = [0] * n_slots
+    if initial is None:
+        states = [fresh() for _ in range(n_slots)]
+        plies = [0] * n_slots
+    else:  # the slots start spread over whole games (positions and their ply numbers given by the caller)
+        states = [from_record(initial[i]) for i in range(n_slots)]
+        plies = [int(p) for p in initial_plies]
     one = torch.tensor(1, dtype=torch.float32)
     positions = 0
     t0 = 0.0
@@ -101,14 +113,18 @@ def _work(R, start_rec, n_slots, steps, warmup, max_plies, seed, barrier, out_q)
     out_q.put((positions, dt))
 
 
-def run(R, start_rec, n_games, steps, warmup, n_procs, max_plies=2048, seed=0x5EED):
-    """positions/s over all processes for `steps` plies of `n_games` resident games."""
+def run(R, start_rec, n_games, steps, warmup, n_procs, max_plies=2048, seed=0x5EED, initial=None, initial_plies=None):
+    """positions/s over all processes for `steps` plies of `n_games` resident games.  initial [n_games][REC] +
+    initial_plies [n_games]: the positions the slots start from (default: every slot at the start record)."""
     ctx = mp.get_context("spawn")
     n_procs = max(1, min(n_procs, n_games))
     sizes = [n_games // n_procs + (1 if i < n_games % n_procs else 0) for i in range(n_procs)]
     barrier = ctx.Barrier(n_procs + 1)
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(R, start_rec, sizes[i], steps, warmup, max_plies, seed + i, barrier, q))
+    offs = [sum(sizes[:i]) for i in range(n_procs)]
+    procs = [ctx.Process(target=_worker, args=(R, start_rec, sizes[i], steps, warmup, max_plies, seed + i, barrier, q,
+                                               None if initial is None else initial[offs[i]: offs[i] + sizes[i]],
+                                               None if initial is None else initial_plies[offs[i]: offs[i] + sizes[i]]))
              for i in range(n_procs)]
     for p in procs:
         p.start()
