@@ -59,11 +59,20 @@ class InferenceNet:
 
     The wrapped module is left untouched (fp32, trainable); call refresh() after its weights change."""
 
-    def __init__(self, net: PolicyValueNet, bf16: bool = True, fused: bool = True):
+    def __init__(self, net: PolicyValueNet, bf16: bool = True, fused: bool = True, split_policy_linear: bool = False):
+        """split_policy_linear (fp32 only): the 23,520^2 policy Linear -- 1.13 TFLOP per 1,024 leaves, 17 of the 19.4 ms
+        of the fp32 network on the SIMT pipes -- as a bf16 x 3 split product on the tensor cores: W = W1 + W2 + W3 and
+        x = x1 + x2 + x3 in bf16 (24 mantissa bits each way), the six leading cross terms accumulated in fp32 inside
+        three GEMMs.  Every bf16 product is exact in fp32; what remains is the tensor cores' fp32 accumulation, which is
+        not IEEE round-to-nearest over K = 3 x 23,520: measured against an fp64 Linear on B200, strict fp32 is off by
+        6e-7 of the logit scale, this split by 1.2e-5, TF32 and bf16 by orders of magnitude more
+        (tests/test_gpu_mcts.py::test_split_policy_linear_matches_strict_fp32 prints the ladder).  An intermediate
+        precision, NOT the reference's arithmetic: bench.py reports it beside the strict fp32 line, never instead."""
         self.dtype = torch.bfloat16 if bf16 else torch.float32
         self.module = net
         self.device = net.device
         self.fused = bool(fused) and self.device.type == "cuda" and self._fused_ops_work()
+        self.split = bool(split_policy_linear) and not bf16 and self.device.type == "cuda"
         self.refresh()
 
     # ---- weights ----------------------------------------------------------------------------------------
@@ -93,6 +102,15 @@ class InferenceNet:
         self.v_conv = self._conv(m.value[0][0], m.value[0][1])
         self.p_lin = self._head_linear(m.policy[2], m.policy[0][0].out_channels)
         self.v_lin = self._head_linear(m.value[2], m.value[0][0].out_channels)
+        if self.split:
+            w, parts = self.p_lin[0].float(), []
+            for _ in range(3):
+                part = w.to(torch.bfloat16)
+                parts.append(part.t())
+                w = w - part.float()
+            self.p_split = torch.cat(parts, dim=0).contiguous()  # [3K, out]: rows W1^T | W2^T | W3^T
+            self.p_lin = (None, self.p_lin[1])
+            del w, parts
 
     def _fused_ops_work(self) -> bool:
         try:
@@ -125,7 +143,18 @@ class InferenceNet:
             x = self._conv_add_relu(self._conv_relu(x, a), b, x)
         p = self._conv_relu(x, self.p_conv).permute(0, 2, 3, 1).reshape(n, -1)  # (h, w, c) order: a view
         v = self._conv_relu(x, self.v_conv).permute(0, 2, 3, 1).reshape(n, -1)
-        logits = torch.nn.functional.linear(p, self.p_lin[0], self.p_lin[1])
+        if self.split:
+            K = p.shape[1]
+            x1 = p.to(torch.bfloat16)
+            r = p - x1.float()
+            x2 = r.to(torch.bfloat16)
+            x3 = (r - x2.float()).to(torch.bfloat16)
+            logits = torch.mm(torch.cat([x1, x1, x1], dim=1), self.p_split, out_dtype=torch.float32)  # x1 (W1 + W2 + W3)
+            logits += torch.mm(torch.cat([x2, x2], dim=1), self.p_split[: 2 * K], out_dtype=torch.float32)  # x2 (W1 + W2)
+            logits += torch.mm(x3, self.p_split[:K], out_dtype=torch.float32)  # x3 W1
+            logits += self.p_lin[1]
+        else:
+            logits = torch.nn.functional.linear(p, self.p_lin[0], self.p_lin[1])
         value = torch.tanh(torch.nn.functional.linear(v, self.v_lin[0], self.v_lin[1]))
         return logits.float(), value.float()
 

