@@ -354,10 +354,12 @@ def run_ours(args) -> None:
     e0.record()
     for _ in range(args.steps):
         step()
-    if rank == 0:
-        sampler.poll_once()  # the host runs ahead of the device: the queue is still full, a sample under load
     env.join()  # the main stream waits for the last expansion: every step's tensors are complete
     e1.record()
+    if rank == 0:
+        # the host runs ahead of the device: the queue is still full, a sample under load -- taken AFTER the closing
+        # event is enqueued, so that a slow NVML call cannot stretch a short timed region
+        sampler.poll_once()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
@@ -365,6 +367,9 @@ def run_ours(args) -> None:
     ex_n, ex_ms, ru_ms = ctypes.c_int(0), ctypes.c_double(0.0), ctypes.c_double(0.0)
     _lib.check(L.fpc_profile_read(ctypes.byref(ex_n), ctypes.byref(ex_ms), ctypes.byref(ru_ms)))
     _lib.check(L.fpc_profile_enable(0))
+
+    # the resident games as the timed region left them (whole-game mix): the e2e leg starts from the same positions
+    snap = (env.boards.cpu(), env.game.cpu(), env.ply.cpu())
 
     # rules only (movegen + legal filter + result + make, no dense tensors): the integer-bound part
     env_counters = env.counters.clone()
@@ -426,9 +431,10 @@ def run_ours(args) -> None:
     if not ctx:
         raise SystemExit(L.fpc_last_error().decode())
     rec = env.geom.record_bytes
-    h_boards = torch.from_numpy(np.broadcast_to(start, (N_GAMES, rec)).copy()).pin_memory()
-    h_game = torch.arange(rank * N_GAMES, (rank + 1) * N_GAMES, dtype=torch.int64).pin_memory()
-    h_ply = torch.zeros(N_GAMES, dtype=torch.int32).pin_memory()
+    h_boards = snap[0].contiguous().pin_memory()  # the same whole-game position mix as the device-resident loop
+    h_game = snap[1].contiguous().pin_memory()
+    h_ply = snap[2].contiguous().pin_memory()
+    assert h_boards.shape == (N_GAMES, rec)
     h_counts = torch.zeros(N_GAMES, dtype=torch.int32).pin_memory()
     h_status = torch.zeros(N_GAMES, dtype=torch.int32).pin_memory()
     h_start = torch.from_numpy(start.copy()).pin_memory()
@@ -485,7 +491,7 @@ def run_ours(args) -> None:
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "fpc_host_playout_step: boards/game ids/plies from pinned host memory and back every "
+                    "note": "fpc_host_playout_step (same whole-game position mix as `value`): boards/game ids/plies from pinned host memory and back every "
                             "step (the call returns when they have landed); planes+mask are left on the device "
                             "as the reference's device='cuda' does, their expansion overlapping the next step"},
             "gpu_launches": 2 * args.steps,
