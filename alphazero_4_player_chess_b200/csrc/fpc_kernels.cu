@@ -286,6 +286,14 @@ static int xknob(const char *name) {
 }
 template <class G>
 static void launch_rules_x(int n, cudaStream_t st, const ObserveParams &p) {
+  // FPC_X_RSMEM = KB of (unused) dynamic shared memory per rules CTA: caps how many of them an SM holds
+  const int dyn = xknob("FPC_X_RSMEM") * 1024;
+  if (dyn) {
+    static bool set = false;
+    if (!set) cudaFuncSetAttribute(rules_kernel<G, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), set = true;
+    rules_kernel<G, 4><<<(n + 3) / 4, 128, dyn, st>>>(p);
+    return;
+  }
   switch (xknob("FPC_X_RWARPS")) {
     case 1: rules_kernel<G, 1><<<n, 32, 0, st>>>(p); break;
     case 2: rules_kernel<G, 2><<<(n + 1) / 2, 64, 0, st>>>(p); break;
