@@ -284,8 +284,14 @@ static int xknob(const char *name) {
   const char *e = getenv(name);
   return e ? atoi(e) : 0;
 }
+__global__ void delay_kernel(int us) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < (long long)us * 1965) __nanosleep(200);
+}
 template <class G>
 static void launch_rules_x(int n, cudaStream_t st, const ObserveParams &p) {
+  // FPC_X_RDELAY = microseconds the rules kernel is held back on its stream (one idle thread spins first)
+  if (xknob("FPC_X_RDELAY")) delay_kernel<<<1, 1, 0, st>>>(xknob("FPC_X_RDELAY"));
   // FPC_X_RSMEM = KB of (unused) dynamic shared memory per rules CTA: caps how many of them an SM holds
   const int dyn = xknob("FPC_X_RSMEM") * 1024;
   if (dyn) {

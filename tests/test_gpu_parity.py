@@ -584,3 +584,21 @@ def test_full_size_properties():
             own = ((sq >= 0x80) & (((sq >> 5) & 3) == turn[:, None])).view(n, 1, R, R)
             assert bool((mask.amax(dim=1, keepdim=True) <= own.float()).all())
     assert int(env.counters[0].item()) == 64 * n
+
+
+def test_playout_stepper_is_the_same_call():
+    """BatchedEnv.playout_stepper (arguments resolved once) plays the same games as playout_step."""
+    start = start_record("STANDARD", castling=True)
+    a, b = BatchedEnv(14, 256), BatchedEnv(14, 256)
+    a.reset_playout(start)
+    b.reset_playout(start)
+    step = b.playout_stepper(seed=SEED, max_plies=64, planes=True, mask=True, async_dense=True)
+    for _ in range(80):
+        a.playout_step(seed=SEED, max_plies=64, planes=True, mask=True, async_dense=True)
+        step()
+    a.join()
+    b.join()
+    torch.cuda.synchronize()
+    for name in ("boards", "game", "ply", "counts", "status", "counters"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.equal(a.planes_buffer(), b.planes_buffer()) and torch.equal(a.mask_buffer(), b.mask_buffer())
