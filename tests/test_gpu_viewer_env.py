@@ -168,3 +168,33 @@ def test_native_env_store_and_its_own_dlpack_export():
     assert torch.equal(planes, keep)
     del planes, mask, counts, status, moves, boards, ply
     assert not _lib.lib().fpc_env_dlpack(None, _lib.ENV_PLANES)
+
+
+def test_dropin_expand_nodes_in_chunks(az):
+    """Node.ExpandNodes with more children than one trip of the host-buffer context holds (16,384): 1,000 roots x 20
+    moves = 20,000 children made and observed in two chunks; sampled children equal the oracle's make-move and carry the
+    right legal moves and result."""
+    R = 14
+    az.set_board_size(R)
+    o = oracle_for(R)
+    start = start_record("STANDARD")
+    n_roots = 1000
+    roots = [board_from_record(az, start, R) for _ in range(n_roots)]
+    rec0 = np.frombuffer(roots[0].record(), dtype=np.uint8).copy()
+    legal = sorted((int(m) for m in o.legal_moves(rec0)), key=lambda m: (o.move_flat_index(m), (m >> 24) & 0xff))
+    flats = [o.move_flat_index(m) for m in legal]
+    nodes = [az.Node(3.0, b, visit_count=1) for b in roots]
+    nsq = R * R
+    nz = [[i, f // nsq, (f % nsq) // R, f % R] for i in range(n_roots) for f in flats]
+    values = [1.0 / len(flats)] * len(nz)
+    az.Node.ExpandNodes(nodes, torch.zeros(1), nz, values, az.BoardPool(1))
+    assert len(nz) > 16384
+    for i in (0, 1, 499, 818, 819, 820, 999):  # 819 * 20 = 16,380: the chunk boundary falls inside root 819
+        ch = nodes[i].GetChildren()
+        assert [c.GetMoveMade().GetFlatIndex() for c in ch] == flats
+        for c, f in zip(ch, flats):
+            crec = np.frombuffer(c.GetState().record(), dtype=np.uint8)
+            assert np.array_equal(crec, o.make_index(rec0, f))
+            want = sorted((int(m) for m in o.legal_moves(crec)), key=lambda m: (o.move_flat_index(m), (m >> 24) & 0xff))
+            assert [m.image() for m in c.GetState().GetLegalMoves()] == want
+            assert int(c.GetState().GetGameResult()) == o.game_result(crec)[0]
