@@ -177,18 +177,47 @@ __device__ __forceinline__ void softmax_merge(float &m, float &s, float om, floa
 }
 
 template <class G>
-__global__ void __launch_bounds__(EXP_THREADS) tree_expand_backup_kernel(const fpc_tree T, const float *logits, const float *values) {
+__global__ void __launch_bounds__(EXP_THREADS, 8) tree_expand_backup_kernel(const fpc_tree T, const float *logits, const float *values) {
   __shared__ float red_m[EXP_WARPS], red_s[EXP_WARPS];
   __shared__ double red_d[EXP_WARPS];
   __shared__ int red_i[EXP_WARPS];
   __shared__ float s_max, s_sum;
   __shared__ double s_msum;
   __shared__ int s_base;
+  constexpr int ANC_MAX = 64;
+  __shared__ int s_anc[ANC_MAX];
+  __shared__ int s_nanc, s_anc_next;
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // every per-game scalar is requested at once (one memory latency instead of a chain of them), and so are the legal
+  // moves (rows past the count hold stale moves of earlier leaves: valid memory, ignored below)
   const int leaf = T.leaf[g];
+  const int status = T.leaf_status[g];
+  const int cnt = T.leaf_counts[g];
+  const int k = T.k[g] & 3;
+  const float value_in = values[g];
+  constexpr int PER = (MAX_MOVES + EXP_THREADS - 1) / EXP_THREADS;
+  int flat_in[PER], prev_in[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) {
+    const int i = tid + q * EXP_THREADS;
+    flat_in[q] = i < MAX_MOVES ? T.leaf_flat[(size_t)g * MAX_MOVES + i] : -1;
+    prev_in[q] = (i > 0 && i < MAX_MOVES) ? T.leaf_flat[(size_t)g * MAX_MOVES + i - 1] : -1;
+  }
   if (leaf < 0) return;
   const size_t slab = (size_t)g * T.node_cap;
-  const int status = T.leaf_status[g];
+  // The latency-bound tail is prepared while the logits stream: one thread (of the last warp) walks the leaf's ancestors
+  // now -- a chain of dependent loads -- so that the backup at the end is one parallel round of updates; thread 0 has
+  // the node count of the slab in a register by then.
+  if (tid == EXP_THREADS - 32) {
+    int node = leaf, cnt = 0;
+    while (node >= 0 && cnt < ANC_MAX) {
+      s_anc[cnt++] = node;
+      node = T.parent[slab + node];
+    }
+    s_nanc = cnt;
+    s_anc_next = node;  // >= 0 only for a path longer than ANC_MAX
+  }
+  const int nodes_before = tid == 0 ? T.n_nodes[g] : 0;
   const int result = status & FPC_STATUS_RESULT_MASK;
   float value;
   if (result != 0) {
@@ -196,12 +225,9 @@ __global__ void __launch_bounds__(EXP_THREADS) tree_expand_backup_kernel(const f
     value = result == 3 ? 0.0f : -1.0f;
     if (tid == 0) T.dropped[g] = 1;
   } else {
-    value = values[g];
+    value = value_in;
     const float *lg = logits + (size_t)g * G::ASZ;
     // ---- the legal moves' own logits are requested first (scattered, ~20 of them) ---------------------
-    const int cnt = T.leaf_counts[g];
-    const int k = T.k[g] & 3;
-    constexpr int PER = (MAX_MOVES + EXP_THREADS - 1) / EXP_THREADS;
     int flat[PER];
     float lgt[PER];
     bool first[PER];
@@ -210,8 +236,8 @@ __global__ void __launch_bounds__(EXP_THREADS) tree_expand_backup_kernel(const f
       const int i = tid + q * EXP_THREADS;
       flat[q] = -1, lgt[q] = 0.0f, first[q] = false;
       if (i < cnt) {
-        flat[q] = T.leaf_flat[(size_t)g * MAX_MOVES + i];
-        first[q] = i == 0 || T.leaf_flat[(size_t)g * MAX_MOVES + i - 1] != flat[q];  // promotions share an index
+        flat[q] = flat_in[q];
+        first[q] = i == 0 || prev_in[q] != flat[q];  // promotions share an index
         if (first[q]) {
           // policy[plane][r][c] = rot90(net_out, -k)[plane][r][c]: one clockwise quarter turn reads out[i][j] = in[R-1-j][i]
           const int plane = flat[q] / G::NSQ, sq = flat[q] - plane * G::NSQ;
@@ -310,7 +336,7 @@ __global__ void __launch_bounds__(EXP_THREADS) tree_expand_backup_kernel(const f
           all += __syncthreads_count(first[q2] && pr2 != 0.0f);
         }
         if (tid == 0) {
-          int base = T.n_nodes[g];
+          int base = nodes_before;
           if (base + all > T.node_cap) {
             T.error[g] |= ERR_NODE_CAP;
             base = -1;
@@ -340,9 +366,15 @@ __global__ void __launch_bounds__(EXP_THREADS) tree_expand_backup_kernel(const f
     }
   }
   // ---- Node::Backpropagate (node.cpp:133-142): +v at the leaf, sign flips at every ancestor ------
-  if (tid == 0) {
-    double v = (double)value;
-    int node = leaf;
+  __syncthreads();  // the ancestor list is complete (and, when expanding, every child has been written)
+  if (tid < s_nanc) {
+    const int node = s_anc[tid];
+    T.value_sum[slab + node] += (tid & 1) ? -(double)value : (double)value;
+    T.visits[slab + node] += 1;
+  }
+  if (tid == 0 && s_anc_next >= 0) {  // deeper than ANC_MAX: the rest of the path one by one
+    double v = (ANC_MAX & 1) ? -(double)value : (double)value;
+    int node = s_anc_next;
     while (node >= 0) {
       T.value_sum[slab + node] += v;
       T.visits[slab + node] += 1;
