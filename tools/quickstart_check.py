@@ -1,3 +1,5 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from alphazero_4_player_chess_b200.env import BatchedEnv
 from alphazero_4_player_chess_b200.fen import start_record
