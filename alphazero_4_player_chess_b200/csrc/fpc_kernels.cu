@@ -289,7 +289,9 @@ __global__ void delay_kernel(int us) {
   while (clock64() - t0 < (long long)us * 1965) __nanosleep(200);
 }
 template <class G>
-static void launch_rules_x(int n, cudaStream_t st, const ObserveParams &p) {
+static void launch_rules_x(int n, cudaStream_t st, const ObserveParams &p_in) {
+  ObserveParams p = p_in;
+  if (xknob("FPC_X_NOCOUNTERS")) p.counters = nullptr;  // no global atomics on the eight shared counters
   // FPC_X_RDELAY = microseconds the rules kernel is held back on its stream (one idle thread spins first)
   if (xknob("FPC_X_RDELAY")) delay_kernel<<<1, 1, 0, st>>>(xknob("FPC_X_RDELAY"));
   // FPC_X_RSMEM = KB of (unused) dynamic shared memory per rules CTA: caps how many of them an SM holds
