@@ -78,8 +78,12 @@ class ClockSampler:
         self.gpu = gpu_index
         self.sm, self.reasons, self.smax = [], 0, None
         self.stop_flag = threading.Event()
+        self.armed = threading.Event()
         self.thread = None
         self.poll_once = lambda: None
+
+    def arm(self):
+        self.armed.set()
 
     def start(self):
         try:
@@ -105,6 +109,9 @@ class ClockSampler:
             self.poll_once = once  # the main thread also samples at fixed points inside the timed region
 
             def poll():
+                # NVML calls take driver locks that a kernel launch on another thread may have to wait for: the thread
+                # only polls once the timed region's launches are all enqueued (arm()), while the device works them off
+                self.armed.wait()
                 while not self.stop_flag.is_set():
                     once()
                     time.sleep(0.002)
@@ -118,6 +125,7 @@ class ClockSampler:
         if self.thread is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
         self.stop_flag.set()
+        self.armed.set()
         self.thread.join(timeout=1)
         active = sorted(name for name, bit in self.REASONS.items() if self.reasons & bit)
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.smax,
@@ -361,6 +369,7 @@ def run_ours(args) -> None:
         # the host runs ahead of the device: the queue is still full, a sample under load -- taken AFTER the closing
         # event is enqueued, so that a slow NVML call cannot stretch a short timed region
         sampler.poll_once()
+        sampler.arm()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
