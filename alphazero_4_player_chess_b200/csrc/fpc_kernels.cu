@@ -377,14 +377,16 @@ static int launch_observe(ObserveParams p, DenseOut d, cudaStream_t st, F after_
       return after_rules();
     }
   }
-  // is a run of dense calls starting from an idle expansion stream?  (asked before this call enqueues anything on it;
-  // never during stream capture, where querying a stream is not allowed)
+  // Is the caller running ahead of the device (both internal streams still have work queued), or does this call find
+  // one of them idle -- a run of dense calls starting up, or a host that waits for every step's results?  Asked before
+  // this call enqueues anything; never during stream capture, where querying a stream is not allowed (a captured call
+  // counts as running ahead).
   bool side_was_idle = false;
   {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cudaGetLastError(), cap = cudaStreamCaptureStatusActive;
     if (cap == cudaStreamCaptureStatusNone && startup_probe_enabled()) {
-      side_was_idle = cudaStreamQuery(S->side) == cudaSuccess;
+      side_was_idle = cudaStreamQuery(S->side) == cudaSuccess || cudaStreamQuery(S->hi) == cudaSuccess;
       cudaGetLastError();  // "not ready" is reported through the error state
     }
   }
@@ -454,11 +456,13 @@ static int launch_observe(ObserveParams p, DenseOut d, cudaStream_t st, F after_
   CK(cudaGetLastError());
   if (prof && (prof_mask() & 8)) CK(cudaEventRecord(S->prof_ev[2 * S->prof_n + 1], S->side));
   if (prof) ++S->prof_n;
-  // Pipeline start-up.  When the expansion stream is found idle a run of dense calls is (re)starting: the first few
-  // expansions are then followed by a TIMESTAMPED event record instead of a plain one.  Measured on B200
-  // (tools/overlap_probe.py, gpurun_out/xrun23.log): a timestamped record after every expansion costs ~2 us per step in
-  // steady state (76.3 vs 74.2 us) but a loop of 20 steps from an idle device runs at 79 us per step with it and at
-  // ~90 us without -- so it is used for the first STARTUP_CALLS calls only.  (Not during stream capture.)
+  // Which event marks the end of this expansion.  A TIMESTAMPED record is the robust one: measured on B200
+  // (tools/overlap_probe.py, gpurun_out/xrun23.log, xrun26.log) it costs ~2 us per step against a plain record when the
+  // caller runs far ahead of the device (76.3 vs 74.2 us per step), but with the plain record a loop that starts from
+  // an idle device loses ~250 us (20 steps: ~90 vs 79 us per step), and a caller that waits for every step's results
+  // before issuing the next one falls into a mode of 176 us per step (83 us with the timestamped record).  So: the
+  // timestamped record whenever a call finds an internal stream idle, and for the STARTUP_CALLS calls after that; the
+  // plain one only while the caller keeps both streams busy.
   constexpr int STARTUP_CALLS = 8;
   if (side_was_idle) S->startup_left = STARTUP_CALLS;
   S->expand_done[b] = S->startup_left > 0 ? S->expand_done_stamped[b] : S->expand_done_plain[b];
