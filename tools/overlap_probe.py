@@ -8,6 +8,8 @@ from alphazero_4_player_chess_b200 import _lib
 from alphazero_4_player_chess_b200.env import BatchedEnv
 from alphazero_4_player_chess_b200.fen import start_record
 
+if int(os.environ.get("FPC_P_OWNSTREAM", "0")):  # 1: work on a non-blocking torch stream instead of the legacy default stream
+    torch.cuda.set_stream(torch.cuda.Stream())
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 ff = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 L = _lib.lib()
