@@ -602,12 +602,18 @@ def run_ours(args) -> None:
     if rank == 0:
         if mcts is not None:
             out["mcts"] = mcts
+            if world == 1:
+                # the N = 1 point of the configs[4] series (8,192 games x 800 simulations per GPU), beside configs[3]
+                shard = mcts_leg(rank, world, local, shard_of_configs4=True)
+                shard["note"] = ("one GPU's share of configs[4] (8,192 games x 800 simulations): compare with `mcts` of "
+                                 "the runs at N = 2, 4, 8, which sum this over the ranks; fp32 is a 100-simulation sample")
+                out["mcts_configs4_shard"] = shard
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def mcts_leg(rank: int, world: int, local: int) -> dict:
+def mcts_leg(rank: int, world: int, local: int, shard_of_configs4: bool = False) -> dict:
     """M2, batched PUCT self-play search with a random-init ResNet 10 x 128 of the reference architecture in PyTorch.
     N = 1: configs[3] at its stated size, 1,024 games x 400 simulations.  N > 1: configs[4], 8,192 games per GPU x 800
     simulations (bf16 in full; the fp32 line is a 100-simulation sample of the same search: the fp32 network alone
@@ -619,7 +625,8 @@ def mcts_leg(rank: int, world: int, local: int) -> dict:
     from alphazero_4_player_chess_b200.mcts import BatchedMCTS
     from alphazero_4_player_chess_b200.net import InferenceNet, PolicyValueNet
 
-    single = world == 1
+    # shard_of_configs4 (N = 1 only): one GPU's share of configs[4] -- the N = 1 point of the 1/2/4/8 series
+    single = world == 1 and not shard_of_configs4
     n_games = 1024 if single else 8192
     sims_full = 400 if single else 800
     dev = f"cuda:{local}"
@@ -629,7 +636,10 @@ def mcts_leg(rank: int, world: int, local: int) -> dict:
                       "configs[4]: sharded self-play, 8,192 games per GPU x 800 simulations (65,536 games on 8 GPUs)") +
                      ", 14x14 STANDARD roots, C=3, random-init ResNet 10x128 (reference architecture incl. the 23,520^2 "
                      "policy Linear) in PyTorch; one simulation = select -> network -> expand/backup, CUDA-graphed"}
-    for name, bf16 in (("fp32", False), ("fp32_split", False), ("tf32", False), ("bf16", True)):
+    variants = (("fp32", False), ("fp32_split", False), ("tf32", False), ("bf16", True))
+    if shard_of_configs4:
+        variants = (("fp32", False), ("bf16", True))
+    for name, bf16 in variants:
         sims = sims_full if (single or bf16) else (100 if name == "fp32" else 200)
         # "tf32": fp32 weights and activations with TF32 tensor-core matmuls allowed (torch.backends.cuda.matmul.allow_tf32;
         # the convolutions already run TF32 under PyTorch defaults) -- NOT the reference's default, reported beside it
